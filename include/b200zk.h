@@ -1,0 +1,133 @@
+/*
+ * b200zk — C ABI of the B200-native Halo2/KZG polynomial-arithmetic backend.
+ *
+ * This is the drop-in boundary for the ONE hot path of scroll-prover: the
+ * functions a patched `halo2_proofs` crate binds over FFI in place of its Rayon CPU arithmetic.
+ * The reference selects its GPU backend by whole-crate substitution of halo2_proofs
+ * (/root/reference/docker/chain-prover/gpu/Dockerfile:7, /root/reference/Cargo.toml:33-45);
+ * INTEGRATION.md shows the Rust `extern "C"` stub that replaces each halo2_proofs function body.
+ *
+ * Conventions
+ *  - every entry point returns int32: B200ZK_OK (0) or a negative B200ZK_E_*; it never aborts and
+ *    never throws across the boundary; b200zk_last_error(ctx) returns the message of the last
+ *    failure on that context (the reference's Rust side turns it into the panic/assert it had).
+ *  - field elements are raw Montgomery limbs, memcpy-compatible with halo2curves 0.1.0
+ *    `Fr([u64;4])` / `Fq([u64;4])`; points are `G1Affine{x,y}` (64 B, identity = (0,0)) and
+ *    `G1{x,y,z}` Jacobian (96 B, identity z = 0)            (pin: /root/reference/Cargo.lock:1911-1913).
+ *  - every data pointer may be a host pointer OR a device pointer (detected with
+ *    cudaPointerGetAttributes); host data is staged through pinned buffers inside the call.
+ *  - one context per process per GPU (one process per GPU is the deployment model); a context is
+ *    safe to call from several host threads (calls serialise on the context's stream).
+ *  - there is NO CPU fallback: without a CUDA device b200zk_ctx_create fails with B200ZK_E_CUDA.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200ZK_API __attribute__((visibility("default")))
+#else
+#define B200ZK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ZK_OK 0
+#define B200ZK_E_INVALID (-1)   /* bad argument (the reference would assert/panic) */
+#define B200ZK_E_CUDA (-2)      /* CUDA runtime / launch failure, or no device */
+#define B200ZK_E_OOM (-3)       /* device or pinned-host allocation failed */
+#define B200ZK_E_UNSUPPORTED (-4)
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_srs b200zk_srs;
+
+/* SRS tags: which ParamsKZG vector the bases are (commit vs commit_lagrange) */
+#define B200ZK_SRS_G 0u
+#define B200ZK_SRS_G_LAGRANGE 1u
+
+/* coset_mode of b200zk_ntt_fr */
+#define B200ZK_COSET_NONE 0      /* plain best_fft */
+#define B200ZK_COSET_PRE 1       /* a[i] *= zeta^i before the transform  (coeff_to_extended) */
+#define B200ZK_COSET_POST 2      /* a[i] *= zeta^-i after the transform  (extended_to_coeff) */
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* devices/n_devices: CUDA ordinals this context drives; this build drives exactly one per context
+ * (n_devices == 1; multi-GPU = one process and one context per GPU). */
+B200ZK_API int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out);
+B200ZK_API int32_t b200zk_ctx_destroy(b200zk_ctx* ctx);
+B200ZK_API const char* b200zk_last_error(const b200zk_ctx* ctx);
+/* Run all work of this context on the caller's CUDA stream (cudaStream_t cast to void*), e.g. the
+ * current torch stream, so the caller's CUDA events bracket our kernels.  NULL = own stream. */
+B200ZK_API int32_t b200zk_ctx_set_stream(b200zk_ctx* ctx, void* cuda_stream);
+B200ZK_API int32_t b200zk_ctx_synchronize(b200zk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+B200ZK_API int32_t b200zk_ctx_launch_count(const b200zk_ctx* ctx, uint64_t* out);
+
+/* ---- device buffers (lets a caller keep columns resident between calls) --- */
+B200ZK_API int32_t b200zk_buf_alloc(b200zk_ctx* ctx, uint64_t bytes, void** out_dev);
+B200ZK_API int32_t b200zk_buf_free(b200zk_ctx* ctx, void* dev);
+B200ZK_API int32_t b200zk_buf_upload(b200zk_ctx* ctx, void* dev, const void* host, uint64_t bytes);
+B200ZK_API int32_t b200zk_buf_download(b200zk_ctx* ctx, void* host, const void* dev, uint64_t bytes);
+
+/* ---- SRS ------------------------------------------------------------------------------------ */
+/* Replaces holding `ParamsKZG::g` / `g_lagrange` on the host (halo2_proofs/src/poly/kzg/commitment.rs;
+ * reference call sites /root/reference/bin/src/trace_prover.rs:35-36, integration/src/prove.rs:12):
+ * uploads n affine bases once; they stay resident for the life of the handle. */
+B200ZK_API int32_t b200zk_srs_register(b200zk_ctx* ctx, const void* g1_affine, uint64_t n, uint32_t tag, b200zk_srs** out);
+B200ZK_API int32_t b200zk_srs_release(b200zk_ctx* ctx, b200zk_srs* srs);
+B200ZK_API int32_t b200zk_srs_len(const b200zk_srs* srs, uint64_t* out);
+
+/* ---- MSM ------------------------------------------------------------------------------------ */
+/* Replaces halo2_proofs::arithmetic::best_multiexp(coeffs, bases) and therefore
+ * ParamsKZG::commit / commit_lagrange (halo2_proofs/src/arithmetic.rs, poly/kzg/commitment.rs @ e5ddf67,
+ * pin /root/reference/Cargo.lock:1886-1888; reached from /root/reference/integration/src/prove.rs:37-39).
+ * result = sum_{i<n} scalars[i] * srs[i] as a normalised Jacobian point (x, y, 1), or (0, 1, 0) for the
+ * identity.  n must be <= the SRS length (commit over the first n bases); n == 0 gives the identity. */
+B200ZK_API int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars, uint64_t n, void* out_jacobian96);
+/* same with explicit bases (generic best_multiexp; bases are uploaded for the call) */
+B200ZK_API int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96);
+/* sum of `count` Jacobian points (combining per-GPU partial MSMs after the NCCL all-gather) */
+B200ZK_API int32_t b200zk_g1_sum(b200zk_ctx* ctx, const void* jacobian_points, uint64_t count, void* out_jacobian96);
+/* out[i] = scalars[i] * G1 generator, affine (ParamsKZG::setup's g / g_lagrange generation) */
+B200ZK_API int32_t b200zk_g1_generator_mul_batch(b200zk_ctx* ctx, const void* scalars, uint64_t n, void* out_affine);
+
+/* ---- NTT ------------------------------------------------------------------------------------ */
+/* Replaces halo2_proofs::arithmetic::best_fft::<Fr, Fr>(a, omega, log_n) (arithmetic.rs @ e5ddf67):
+ * in place, natural order in and out, a.len() == 1 << log_n, A[j] = sum_i a[i] omega^(ij).
+ * inverse_scale != 0 additionally multiplies every output by (2^log_n)^-1 (EvaluationDomain::ifft).
+ * coset_mode fuses distribute_powers_zeta (poly/domain.rs): PRE for coeff_to_extended, POST for
+ * extended_to_coeff.  omega must be a primitive 2^log_n-th root of unity (32 B Montgomery). */
+B200ZK_API int32_t b200zk_ntt_fr(b200zk_ctx* ctx, void* data, uint32_t log_n, const void* omega32, int inverse_scale, int coset_mode);
+/* Out-of-place form with zero padding: in has 2^log_in elements (log_in <= log_n), out has 2^log_n.
+ * EvaluationDomain::coeff_to_extended == (log_in = k, log_n = extended_k, omega = extended_omega, PRE). */
+B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t log_in, void* out, uint32_t log_n,
+                          const void* omega32, int inverse_scale, int coset_mode);
+
+/* ---- polynomial batch ops (halo2_proofs Polynomial +,-,*scalar / parallelize loops) ---------- */
+B200ZK_API int32_t b200zk_poly_add(b200zk_ctx* ctx, void* r, const void* a, const void* b, uint64_t n);          /* r = a + b */
+B200ZK_API int32_t b200zk_poly_sub(b200zk_ctx* ctx, void* r, const void* a, const void* b, uint64_t n);          /* r = a - b */
+B200ZK_API int32_t b200zk_poly_mul(b200zk_ctx* ctx, void* r, const void* a, const void* b, uint64_t n);          /* r = a .* b */
+B200ZK_API int32_t b200zk_poly_scale(b200zk_ctx* ctx, void* r, const void* a, const void* s32, uint64_t n);      /* r = s * a */
+B200ZK_API int32_t b200zk_poly_axpy(b200zk_ctx* ctx, void* r, const void* a, const void* s32, const void* b, uint64_t n); /* r = s*a + b */
+/* arithmetic::eval_polynomial(poly, point) */
+B200ZK_API int32_t b200zk_eval_poly(b200zk_ctx* ctx, const void* poly, uint64_t n, const void* point32, void* out32);
+/* ff::BatchInvert on a slice: zeros stay zero */
+B200ZK_API int32_t b200zk_batch_invert(b200zk_ctx* ctx, void* data, uint64_t n);
+/* arithmetic::kate_division: q (n-1 coeffs) = a (n coeffs) / (X - b) */
+B200ZK_API int32_t b200zk_kate_division(b200zk_ctx* ctx, void* q, const void* a, uint64_t n, const void* b32);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* element-wise Fr/Fq Montgomery product of two arrays on the device (field-layer parity tests) */
+B200ZK_API int32_t b200zk_debug_field_op(b200zk_ctx* ctx, int field /*0 Fr,1 Fq*/, int op /*0 mul,1 add,2 sub,3 inv*/,
+                              void* r, const void* a, const void* b, uint64_t n);
+/* MSM tuning knobs (window bits; 0 = auto) and last-call statistics, for bench/roofline reporting */
+B200ZK_API int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c);
+B200ZK_API int32_t b200zk_msm_last_stats(const b200zk_ctx* ctx, uint32_t* window_bits, uint32_t* n_windows, uint64_t* n_bucket_adds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

@@ -1,0 +1,403 @@
+"""scroll-prover_b200 — B200-native Halo2/KZG polynomial-arithmetic backend (host-side Python driver).
+
+This package is the pytest/bench driver over the C ABI in include/b200zk.h (libb200zk.so, hand-written
+sm_100a CUDA).  It mirrors the names and argument meaning of the halo2_proofs functions the library
+replaces (scroll-tech/halo2 @ e5ddf67, pin /root/reference/Cargo.lock:1886-1888):
+
+    best_multiexp(coeffs, bases)            halo2_proofs::arithmetic::best_multiexp
+    best_fft(a, omega, log_n)               halo2_proofs::arithmetic::best_fft
+    EvaluationDomain(j, k)                  halo2_proofs::poly::EvaluationDomain::new
+        .lagrange_to_coeff / .coeff_to_extended / .extended_to_coeff
+    ParamsKZG(g, g_lagrange)                halo2_proofs::poly::kzg::commitment::ParamsKZG
+        .commit / .commit_lagrange
+    eval_polynomial / kate_division / batch_invert
+
+Field elements are numpy uint64 arrays (n, 4) of raw Montgomery limbs (memcpy-compatible with
+halo2curves Fr); affine points (n, 8); a G1 result is a (12,) normalised Jacobian (x, y, 1).
+torch CUDA tensors (uint8/int64 storage) can be passed wherever an array is accepted: their
+device pointer is handed to the library unchanged.
+
+There is NO CPU fallback and this package never imports oracle/: if libb200zk.so is missing or
+no CUDA device is present, constructing a Context raises.
+
+(The directory name contains a hyphen, as the task layout requires; import it with
+ importlib.import_module("scroll-prover_b200") — tests/conftest.py and bench.py do that.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+_R_MONT = 1 << 256
+FR_S = 28
+_ROOT_OF_UNITY = pow(7, (R_MOD - 1) >> FR_S, R_MOD)
+_ZETA = pow(7, 2 * (R_MOD - 1) // 3, R_MOD)
+
+OK, E_INVALID, E_CUDA, E_OOM, E_UNSUPPORTED = 0, -1, -2, -3, -4
+SRS_G, SRS_G_LAGRANGE = 0, 1
+COSET_NONE, COSET_PRE, COSET_POST = 0, 1, 2
+
+
+class B200zkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200zk error {code}: {msg}")
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not built; run `python scroll-prover_b200/build.py` (needs nvcc). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    sig = {
+        "b200zk_ctx_create": [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)],
+        "b200zk_ctx_destroy": [vp],
+        "b200zk_ctx_set_stream": [vp, vp],
+        "b200zk_ctx_synchronize": [vp],
+        "b200zk_ctx_launch_count": [vp, C.POINTER(u64)],
+        "b200zk_buf_alloc": [vp, u64, C.POINTER(vp)],
+        "b200zk_buf_free": [vp, vp],
+        "b200zk_buf_upload": [vp, vp, vp, u64],
+        "b200zk_buf_download": [vp, vp, vp, u64],
+        "b200zk_srs_register": [vp, vp, u64, u32, C.POINTER(vp)],
+        "b200zk_srs_release": [vp, vp],
+        "b200zk_srs_len": [vp, C.POINTER(u64)],
+        "b200zk_msm_g1": [vp, vp, vp, u64, vp],
+        "b200zk_msm_g1_bases": [vp, vp, vp, u64, vp],
+        "b200zk_g1_sum": [vp, vp, u64, vp],
+        "b200zk_g1_generator_mul_batch": [vp, vp, u64, vp],
+        "b200zk_ntt_fr": [vp, vp, u32, vp, C.c_int, C.c_int],
+        "b200zk_ntt_fr_ext": [vp, vp, u32, vp, u32, vp, C.c_int, C.c_int],
+        "b200zk_poly_add": [vp, vp, vp, vp, u64],
+        "b200zk_poly_sub": [vp, vp, vp, vp, u64],
+        "b200zk_poly_mul": [vp, vp, vp, vp, u64],
+        "b200zk_poly_scale": [vp, vp, vp, vp, u64],
+        "b200zk_poly_axpy": [vp, vp, vp, vp, vp, u64],
+        "b200zk_eval_poly": [vp, vp, u64, vp, vp],
+        "b200zk_batch_invert": [vp, vp, u64],
+        "b200zk_kate_division": [vp, vp, vp, u64, vp],
+        "b200zk_debug_field_op": [vp, C.c_int, C.c_int, vp, vp, vp, u64],
+        "b200zk_msm_set_window": [vp, u32],
+        "b200zk_msm_last_stats": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    lib.b200zk_last_error.argtypes = [vp]
+    lib.b200zk_last_error.restype = C.c_char_p
+    return lib
+
+
+ABI_SYMBOLS = [
+    "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
+    "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
+    "b200zk_srs_register", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
+    "b200zk_g1_generator_mul_batch", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_poly_add", "b200zk_poly_sub",
+    "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
+    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_msm_set_window", "b200zk_msm_last_stats",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+# ---------------------------------------------------------------- pointer helpers
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    """(void*, keepalive) of a numpy array or a torch tensor (host or CUDA)."""
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        assert x.is_contiguous()
+        return C.c_void_p(x.data_ptr()), x
+    a = np.ascontiguousarray(x)
+    return C.c_void_p(a.ctypes.data), a
+
+
+def fr_from_int(v: int) -> np.ndarray:
+    v = (v % R_MOD) * _R_MONT % R_MOD
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def fr_to_int(a) -> int:
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(x) << (64 * i) for i, x in enumerate(a)) * pow(_R_MONT, -1, R_MOD) % R_MOD
+
+
+class Context:
+    """One per process per GPU (b200zk_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        devs = (C.c_int * 1)(device)
+        rc = lib().b200zk_ctx_create(devs, 1, C.byref(self._h))
+        if rc != OK:
+            raise B200zkError(rc, "b200zk_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().b200zk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise B200zkError(rc, lib().b200zk_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(lib().b200zk_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._ck(lib().b200zk_ctx_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._ck(lib().b200zk_ctx_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # ---- SRS / MSM
+    def srs_register(self, bases, tag: int = SRS_G) -> "Srs":
+        return Srs(self, bases, tag)
+
+    def msm_set_window(self, c: int):
+        self._ck(lib().b200zk_msm_set_window(self._h, c))
+
+    def msm_last_stats(self):
+        c, w, a = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        self._ck(lib().b200zk_msm_last_stats(self._h, C.byref(c), C.byref(w), C.byref(a)))
+        return {"window_bits": c.value, "n_windows": w.value, "n_bucket_adds": a.value}
+
+    def best_multiexp(self, coeffs, bases) -> np.ndarray:
+        """arithmetic::best_multiexp(coeffs, bases): panics (AssertionError) if lengths differ."""
+        n = _count(coeffs, 32)
+        assert n == _count(bases, 64), "assert_eq!(coeffs.len(), bases.len())"
+        out = np.zeros(12, np.uint64)
+        pc, k1 = _ptr(coeffs)
+        pb, k2 = _ptr(bases)
+        self._ck(lib().b200zk_msm_g1_bases(self._h, pb, pc, n, out.ctypes.data))
+        return out
+
+    def g1_sum(self, jac_points) -> np.ndarray:
+        cnt = _count(jac_points, 96)
+        out = np.zeros(12, np.uint64)
+        p, k = _ptr(jac_points)
+        self._ck(lib().b200zk_g1_sum(self._h, p, cnt, out.ctypes.data))
+        return out
+
+    def g1_generator_mul_batch(self, scalars, out=None):
+        n = _count(scalars, 32)
+        if out is None:
+            out = np.zeros((n, 8), np.uint64)
+        ps, k1 = _ptr(scalars)
+        po, k2 = _ptr(out)
+        self._ck(lib().b200zk_g1_generator_mul_batch(self._h, ps, n, po))
+        return out
+
+    # ---- NTT
+    def best_fft(self, a, omega, log_n: int, inverse_scale: bool = False, coset_mode: int = COSET_NONE):
+        """arithmetic::best_fft(a, omega, log_n) in place (numpy arrays are transformed in place too)."""
+        assert _count(a, 32) == 1 << log_n, "assert_eq!(a.len(), 1 << log_n)"
+        pa, k1 = _ptr(a)
+        po, k2 = _ptr(omega)
+        self._ck(lib().b200zk_ntt_fr(self._h, pa, log_n, po, int(inverse_scale), coset_mode))
+        if not _is_torch(a) and k1 is not a:
+            a[...] = k1.reshape(np.asarray(a).shape)
+        return a
+
+    def ntt_ext(self, a_in, log_in: int, out, log_n: int, omega, inverse_scale: bool = False, coset_mode: int = COSET_NONE):
+        assert _count(a_in, 32) == 1 << log_in and _count(out, 32) == 1 << log_n
+        pi, k1 = _ptr(a_in)
+        po, k2 = _ptr(out)
+        pw, k3 = _ptr(omega)
+        self._ck(lib().b200zk_ntt_fr_ext(self._h, pi, log_in, po, log_n, pw, int(inverse_scale), coset_mode))
+        return out
+
+    # ---- poly ops
+    def _ew(self, fn, r, *args, n):
+        ptrs = [_ptr(x) for x in (r,) + args]
+        self._ck(fn(self._h, *[p for p, _ in ptrs], n))
+        return r
+
+    def poly_add(self, a, b, out=None):
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        return self._ew(lib().b200zk_poly_add, out, a, b, n=n)
+
+    def poly_sub(self, a, b, out=None):
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        return self._ew(lib().b200zk_poly_sub, out, a, b, n=n)
+
+    def poly_mul(self, a, b, out=None):
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        return self._ew(lib().b200zk_poly_mul, out, a, b, n=n)
+
+    def poly_scale(self, a, s, out=None):
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        return self._ew(lib().b200zk_poly_scale, out, a, s, n=n)
+
+    def poly_axpy(self, a, s, b, out=None):
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        return self._ew(lib().b200zk_poly_axpy, out, a, s, b, n=n)
+
+    def eval_polynomial(self, poly, point) -> np.ndarray:
+        n = _count(poly, 32)
+        out = np.zeros(4, np.uint64)
+        pp, k1 = _ptr(poly)
+        px, k2 = _ptr(point)
+        self._ck(lib().b200zk_eval_poly(self._h, pp, n, px, out.ctypes.data))
+        return out
+
+    def batch_invert(self, data):
+        n = _count(data, 32)
+        p, k = _ptr(data)
+        self._ck(lib().b200zk_batch_invert(self._h, p, n))
+        if not _is_torch(data) and k is not data:
+            data[...] = k.reshape(np.asarray(data).shape)
+        return data
+
+    def kate_division(self, a, b) -> np.ndarray:
+        n = _count(a, 32)
+        assert n >= 1
+        q = np.zeros((n - 1, 4), np.uint64)
+        pa, k1 = _ptr(a)
+        pb, k2 = _ptr(b)
+        self._ck(lib().b200zk_kate_division(self._h, q.ctypes.data if n > 1 else None, pa, n, pb))
+        return q
+
+    def debug_field_op(self, field: int, op: int, a, b):
+        n = _count(a, 32)
+        r = np.zeros((n, 4), np.uint64)
+        pa, k1 = _ptr(a)
+        pb, k2 = _ptr(b)
+        self._ck(lib().b200zk_debug_field_op(self._h, field, op, r.ctypes.data, pa, pb, n))
+        return r
+
+
+def _count(x, elem_bytes: int) -> int:
+    if _is_torch(x):
+        return x.numel() * x.element_size() // elem_bytes
+    a = np.asarray(x)
+    return a.size * a.itemsize // elem_bytes
+
+
+def _like(a):
+    if _is_torch(a):
+        import torch
+
+        return torch.empty_like(a)
+    return np.zeros_like(np.asarray(a))
+
+
+class Srs:
+    """Device-resident bases (b200zk_srs): ParamsKZG::g or ::g_lagrange uploaded once."""
+
+    def __init__(self, ctx: Context, bases, tag: int):
+        self.ctx = ctx
+        self.n = _count(bases, 64)
+        self._h = C.c_void_p()
+        p, k = _ptr(bases)
+        ctx._ck(lib().b200zk_srs_register(ctx._h, p, self.n, tag, C.byref(self._h)))
+
+    def msm(self, scalars, n: int | None = None) -> np.ndarray:
+        n = _count(scalars, 32) if n is None else n
+        out = np.zeros(12, np.uint64)
+        p, k = _ptr(scalars)
+        self.ctx._ck(lib().b200zk_msm_g1(self.ctx._h, self._h, p, n, out.ctypes.data))
+        return out
+
+    def release(self):
+        if self._h:
+            lib().b200zk_srs_release(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+
+class ParamsKZG:
+    """halo2_proofs::poly::kzg::commitment::ParamsKZG<Bn256> with device-resident g / g_lagrange."""
+
+    def __init__(self, ctx: Context, k: int, g, g_lagrange=None):
+        self.ctx, self.k, self.n = ctx, k, 1 << k
+        assert _count(g, 64) == self.n
+        self._g = ctx.srs_register(g, SRS_G)
+        self._gl = ctx.srs_register(g_lagrange, SRS_G_LAGRANGE) if g_lagrange is not None else None
+
+    def commit(self, poly) -> np.ndarray:
+        """ParamsProver::commit(poly, Blind): best_multiexp over g[..poly.len()] (blind ignored for KZG)."""
+        return self._g.msm(poly)
+
+    def commit_lagrange(self, poly) -> np.ndarray:
+        assert self._gl is not None
+        return self._gl.msm(poly)
+
+    def release(self):
+        self._g.release()
+        if self._gl:
+            self._gl.release()
+
+
+class EvaluationDomain:
+    """halo2_proofs::poly::EvaluationDomain::new(j, k) (poly/domain.rs): host constants + device transforms."""
+
+    def __init__(self, ctx: Context, j: int, k: int):
+        self.ctx, self.k = ctx, k
+        self.quotient_poly_degree = j - 1
+        self.n = 1 << k
+        ek = k
+        while (1 << ek) < self.n * self.quotient_poly_degree:
+            ek += 1
+        assert ek <= FR_S
+        self.extended_k = ek
+        eo = pow(_ROOT_OF_UNITY, 1 << (FR_S - ek), R_MOD)
+        om = pow(eo, 1 << (ek - k), R_MOD)
+        self.extended_omega, self.omega = fr_from_int(eo), fr_from_int(om)
+        self.extended_omega_inv, self.omega_inv = fr_from_int(pow(eo, -1, R_MOD)), fr_from_int(pow(om, -1, R_MOD))
+        self.g_coset, self.g_coset_inv = fr_from_int(_ZETA), fr_from_int(_ZETA * _ZETA % R_MOD)
+        self.ifft_divisor = fr_from_int(pow(self.n, -1, R_MOD))
+        self.extended_ifft_divisor = fr_from_int(pow(1 << ek, -1, R_MOD))
+
+    def lagrange_to_coeff(self, a):
+        """ifft(a, omega_inv, k, ifft_divisor) in place."""
+        return self.ctx.best_fft(a, self.omega_inv, self.k, inverse_scale=True)
+
+    def coeff_to_extended(self, a, out=None):
+        """distribute_powers_zeta(into_coset) + zero-extend + best_fft(extended_omega): n -> 2^extended_k."""
+        if out is None:
+            if _is_torch(a):
+                import torch
+
+                out = torch.empty((1 << self.extended_k, 4), dtype=a.dtype, device=a.device)
+            else:
+                out = np.zeros((1 << self.extended_k, 4), np.uint64)
+        return self.ctx.ntt_ext(a, self.k, out, self.extended_k, self.extended_omega, False, COSET_PRE)
+
+    def extended_to_coeff(self, a):
+        """ifft(extended_omega_inv) + distribute_powers_zeta(out of coset); returns the first n*(j-1) coefficients."""
+        self.ctx.best_fft(a, self.extended_omega_inv, self.extended_k, inverse_scale=True, coset_mode=COSET_POST)
+        return a[: self.n * self.quotient_poly_degree]

@@ -1,0 +1,153 @@
+// Shared host-side plumbing of libb200zk: context, error reporting, scratch memory, staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+#include "ff.cuh"
+
+namespace b200zk {
+
+struct TwiddleTable {  // universal per-stage twiddles for one root: tab[2^(u-1) + j] = w_{2^u}^j
+    Fr omega;          // the 2^log_n-th root the table was built for
+    uint32_t log_n;
+    Fr* dev;
+};
+
+struct Scratch {  // grow-only device allocation
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace b200zk
+
+struct b200zk_srs {
+    b200zk_ctx* ctx;
+    void* dev_bases;  // n x 64 B affine (x,y Montgomery Fq)
+    uint64_t n;
+    uint32_t tag;
+};
+
+struct b200zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::recursive_mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // scratch pools
+    b200zk::Scratch ntt_work, stage_in, stage_out, msm_work, misc;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+    std::vector<b200zk::TwiddleTable> tables;
+    // msm knobs / stats
+    uint32_t msm_window = 0;
+    uint32_t last_c = 0, last_windows = 0;
+    uint64_t last_adds = 0;
+};
+
+namespace b200zk {
+
+inline int32_t fail(b200zk_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define B2_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return ::b200zk::fail(ctx, e__ == cudaErrorMemoryAllocation ? B200ZK_E_OOM : B200ZK_E_CUDA,      \
+                                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define B2_TRY(expr)                    \
+    do {                                \
+        int32_t rc__ = (expr);          \
+        if (rc__ != B200ZK_OK) return rc__; \
+    } while (0)
+
+#define B2_LAUNCH_CHECK(ctx)                 \
+    do {                                     \
+        (ctx)->launches++;                   \
+        B2_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
+
+inline int32_t scratch_reserve(b200zk_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return B200ZK_OK;
+    if (s.p) {
+        B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2_CUDA(ctx, cudaFree(s.p));
+        s.p = nullptr;
+        s.cap = 0;
+    }
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&s.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&s.p, want);
+    }
+    if (e != cudaSuccess) return fail(ctx, B200ZK_E_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    s.cap = want;
+    return B200ZK_OK;
+}
+
+inline bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Copy host->device (pageable or pinned) on the context stream.
+inline int32_t h2d(b200zk_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    if (!bytes) return B200ZK_OK;
+    B2_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200ZK_OK;
+}
+inline int32_t d2h(b200zk_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (!bytes) return B200ZK_OK;
+    B2_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// Input staging: returns a device pointer holding `bytes` of `p` (p itself if already on device).
+inline int32_t stage_in(b200zk_ctx* ctx, Scratch& s, const void* p, size_t bytes, const void** out) {
+    if (is_device_ptr(p)) {
+        *out = p;
+        return B200ZK_OK;
+    }
+    B2_TRY(scratch_reserve(ctx, s, bytes));
+    B2_TRY(h2d(ctx, s.p, p, bytes));
+    *out = s.p;
+    return B200ZK_OK;
+}
+
+struct Guard {
+    std::lock_guard<std::recursive_mutex> lk;
+    explicit Guard(b200zk_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+// implemented in ntt.cu / msm.cu / poly.cu
+int32_t ntt_run(b200zk_ctx* ctx, const Fr* in, uint32_t log_in, Fr* out, uint32_t log_n, const Fr& omega,
+                int inverse_scale, int coset_mode);
+
+}  // namespace b200zk

@@ -1,0 +1,454 @@
+// BN254 G1 multi-scalar multiplication (Pippenger bucket method) for sm_100a.
+//
+// Device replacement for halo2_proofs::arithmetic::best_multiexp / multiexp_serial and therefore
+// ParamsKZG::commit / commit_lagrange (halo2_proofs/src/arithmetic.rs, src/poly/kzg/commitment.rs @
+// scroll-tech/halo2 e5ddf67, pin /root/reference/Cargo.lock:1886-1888; reached from
+// /root/reference/integration/src/prove.rs:37-39).  The result is the same group element
+// sum_i s_i * P_i, returned normalised, so its bytes equal the reference's `to_affine()` output.
+//
+// Pipeline (DESIGN.md "MSM"); all of it on the context stream, no host synchronisation inside:
+//   1 msm_count     scalar -> canonical (one Montgomery product), signed c-bit digits, per-bucket histogram
+//   2 scan          exclusive prefix sum of the W * 2^(c-1) bucket counts
+//   3 msm_scatter   counting-sort of (point index | sign) into bucket order
+//   4 msm_accumulate  load-balanced segmented reduction: every thread owns L consecutive sorted entries and
+//                   adds affine bases into an XYZZ accumulator (8M+2S per add); buckets wholly inside a
+//                   chunk are stored directly, chunk-straddling runs go to a partial list
+//   5 msm_combine   partial runs of the same bucket are summed
+//   6 bucket_reduce per-window sum_b b * B_b: groups of 32 buckets by running sums, then a log-depth
+//                   tree with power-of-two doublings
+//   7 msm_finish    Horner over windows, normalisation to (x, y, 1)
+// Zero digits are skipped (witness columns are mostly zeros / small values).
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace b200zk {
+
+static constexpr uint32_t PART_INVALID = 0x3fffffffu;
+static constexpr uint32_t PART_STARTS = 0x80000000u;
+static constexpr uint32_t PART_ENDS = 0x40000000u;
+static constexpr int ACC_L = 64;        // sorted entries per accumulate thread
+static constexpr int GROUP = 32;        // buckets per first-level reduction group
+
+struct MsmPlan {
+    uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
+    uint64_t NB;        // W * B
+    uint32_t g, G;      // reduction group size, groups per window
+};
+
+__device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    x.l.v[0] = a.x; x.l.v[1] = a.y; x.l.v[2] = a.z; x.l.v[3] = a.w;
+    x.l.v[4] = b.x; x.l.v[5] = b.y; x.l.v[6] = b.z; x.l.v[7] = b.w;
+    y.l.v[0] = c.x; y.l.v[1] = c.y; y.l.v[2] = c.z; y.l.v[3] = c.w;
+    y.l.v[4] = d.x; y.l.v[5] = d.y; y.l.v[6] = d.z; y.l.v[7] = d.w;
+}
+
+// signed-digit walk over the canonical scalar; f(w, magnitude, negative) for every non-zero digit
+template <class FN>
+__device__ __forceinline__ void for_each_digit(const Fr& s_mont, uint32_t c, uint32_t W, FN f) {
+    Fr s = s_mont.from_mont();
+    uint32_t l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = s.l.v[i];
+    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t v = (l[0] & mask) + carry;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) l[i] = __funnelshift_r(l[i], l[i + 1], c);
+        l[7] >>= c;
+        if (v > half) {
+            uint32_t mag = (1u << c) - v;
+            carry = 1;
+            if (mag) f(w, mag, true);
+        } else {
+            carry = 0;
+            if (v) f(w, v, false);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* hist) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr s = scalars[i];
+        if (s.is_zero()) continue;
+        for_each_digit(s, pl.c, pl.W, [&](uint32_t w, uint32_t mag, bool) { atomicAdd(&hist[(uint64_t)w * pl.B + mag - 1], 1u); });
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_scatter(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* cursor, uint32_t* entries) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr s = scalars[i];
+        if (s.is_zero()) continue;
+        for_each_digit(s, pl.c, pl.W, [&](uint32_t w, uint32_t mag, bool neg) {
+            uint32_t pos = atomicAdd(&cursor[(uint64_t)w * pl.B + mag - 1], 1u);
+            entries[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// ---- exclusive scan of uint32 counts (three kernels) -----------------------------------------
+static constexpr int SCAN_TPB = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_TPB / 32];
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = (lane < SCAN_TPB / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += y;
+        }
+        if (lane < SCAN_TPB / 32) warp_sums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t warp_off = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_TPB / 32 - 1];
+    uint32_t r = warp_off + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) scan_tile_sums(const uint32_t* in, uint64_t n, uint32_t* tile_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < ntiles; ++i) {
+        uint32_t v = tile_sums[i];
+        tile_sums[i] = acc;
+        acc += v;
+    }
+    *grand_total = acc;
+}
+__global__ void __launch_bounds__(SCAN_TPB) scan_apply(const uint32_t* in, uint64_t n, const uint32_t* tile_offs, uint32_t* out,
+                                                     uint32_t* out2) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(s, &total) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) {
+            out[base + k] = off;
+            out2[base + k] = off;
+        }
+        off += v[k];
+    }
+}
+
+// ---- bucket accumulation ------------------------------------------------------------------------
+__device__ __forceinline__ void st_xyzz(XYZZ* p, const XYZZ& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const Fq* f = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        q[2 * k] = make_uint4(f[k].l.v[0], f[k].l.v[1], f[k].l.v[2], f[k].l.v[3]);
+        q[2 * k + 1] = make_uint4(f[k].l.v[4], f[k].l.v[5], f[k].l.v[6], f[k].l.v[7]);
+    }
+}
+__device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    XYZZ v;
+    Fq* f = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint4 a = q[2 * k], b = q[2 * k + 1];
+        f[k].l.v[0] = a.x; f[k].l.v[1] = a.y; f[k].l.v[2] = a.z; f[k].l.v[3] = a.w;
+        f[k].l.v[4] = b.x; f[k].l.v[5] = b.y; f[k].l.v[6] = b.z; f[k].l.v[7] = b.w;
+    }
+    return v;
+}
+
+// offsets has NB + 1 entries (offsets[NB] = total number of sorted entries M).
+__global__ void __launch_bounds__(256, 2)
+msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+               uint64_t NB, XYZZ* __restrict__ buckets, uint32_t* __restrict__ part_id, XYZZ* __restrict__ part_val,
+               uint64_t nthreads) {
+    uint64_t tau = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tau >= nthreads) return;
+    const uint32_t M = offsets[NB];
+    uint64_t start = tau * ACC_L;
+    part_id[2 * tau] = PART_INVALID;
+    part_id[2 * tau + 1] = PART_INVALID;
+    if (start >= M) return;
+    uint32_t end = (start + ACC_L < M) ? (uint32_t)(start + ACC_L) : M;
+    // largest b with offsets[b] <= start
+    uint64_t lo = 0, hi = NB;  // invariant: offsets[lo] <= start, offsets[hi] > start  (offsets[NB] = M > start)
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = (uint32_t)lo;
+    uint32_t bucket_end = offsets[b + 1];
+    bool run_starts = (offsets[b] == (uint32_t)start);
+    bool first_run = true;
+    XYZZ acc = XYZZ::identity();
+    uint32_t pos = (uint32_t)start;
+    while (true) {
+        bool at_end = (pos == end);
+        if (at_end || pos == bucket_end) {
+            bool run_ends = (pos == bucket_end);
+            if (run_starts && run_ends) {
+                st_xyzz(buckets + b, acc);
+            } else {
+                uint32_t slot = first_run ? 0 : 1;
+                part_id[2 * tau + slot] = b | (run_starts ? PART_STARTS : 0u) | (run_ends ? PART_ENDS : 0u);
+                st_xyzz(part_val + 2 * tau + slot, acc);
+            }
+            if (at_end) break;
+            first_run = false;
+            acc = XYZZ::identity();
+            do { ++b; bucket_end = offsets[b + 1]; } while (bucket_end == pos);  // skip empty buckets
+            run_starts = true;
+        }
+        uint32_t e = entries[pos];
+        Fq px, py;
+        ld_affine(bases + (e & 0x7fffffffu), px, py);
+        if (!(px.is_zero() && py.is_zero())) {
+            if (e & 0x80000000u) py = py.neg();
+            xyzz_madd(acc, px, py);
+        }
+        ++pos;
+    }
+}
+
+// head record of every straddling bucket sums the records up to the one that ends the bucket
+__global__ void __launch_bounds__(128) msm_combine(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
+                                                   uint64_t nrec, XYZZ* __restrict__ buckets) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    uint32_t id = part_id[r];
+    if ((id & PART_INVALID) == PART_INVALID || !(id & PART_STARTS)) return;
+    XYZZ sum = ld_xyzz(part_val + r);
+    uint64_t k = r;
+    while (!(id & PART_ENDS)) {
+        ++k;
+        if (k >= nrec) break;
+        id = part_id[k];
+        if ((id & PART_INVALID) == PART_INVALID) { id = 0; continue; }
+        XYZZ v = ld_xyzz(part_val + k);
+        xyzz_add(sum, v);
+    }
+    st_xyzz(buckets + (part_id[r] & PART_INVALID), sum);
+}
+
+// ---- bucket reduction ---------------------------------------------------------------------------
+// group j of window w covers bucket values j*g+1 .. j*g+g:  R = sum B_b,  Wt = sum (b - j*g) B_b
+__global__ void __launch_bounds__(128) msm_group_reduce(const XYZZ* __restrict__ buckets, MsmPlan pl, XYZZ* __restrict__ grpR,
+                                                        XYZZ* __restrict__ grpW) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)pl.W * pl.G;
+    if (t >= total) return;
+    uint32_t w = (uint32_t)(t / pl.G), j = (uint32_t)(t % pl.G);
+    const XYZZ* bk = buckets + (uint64_t)w * pl.B + (uint64_t)j * pl.g;
+    XYZZ run = XYZZ::identity(), ws = XYZZ::identity();
+    for (uint32_t i = pl.g; i-- > 0;) {
+        XYZZ v = ld_xyzz(bk + i);
+        xyzz_add(run, v);
+        xyzz_add(ws, run);
+    }
+    st_xyzz(grpR + t, run);
+    st_xyzz(grpW + t, ws);
+}
+
+// level l: segment i (multiple of 2^(l+1)) absorbs segment i + 2^l:  R += R',  Wt += Wt' + (2^l * g) R'
+__global__ void __launch_bounds__(128) msm_tree_level(MsmPlan pl, uint32_t level, uint32_t log_g, XYZZ* __restrict__ grpR,
+                                                      XYZZ* __restrict__ grpW) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t pairs = pl.G >> (level + 1);
+    uint64_t total = (uint64_t)pl.W * pairs;
+    if (t >= total) return;
+    uint32_t w = (uint32_t)(t / pairs), k = (uint32_t)(t % pairs);
+    uint64_t i = (uint64_t)w * pl.G + ((uint64_t)k << (level + 1)), i2 = i + (1ull << level);
+    XYZZ r1 = ld_xyzz(grpR + i), r2 = ld_xyzz(grpR + i2);
+    XYZZ w1 = ld_xyzz(grpW + i), w2 = ld_xyzz(grpW + i2);
+    xyzz_add(w1, w2);
+    XYZZ sh = r2;
+    for (uint32_t d = 0; d < level + log_g; ++d) sh = xyzz_dbl(sh);
+    xyzz_add(w1, sh);
+    xyzz_add(r1, r2);
+    st_xyzz(grpR + i, r1);
+    st_xyzz(grpW + i, w1);
+}
+
+__global__ void msm_finish(MsmPlan pl, const XYZZ* __restrict__ grpW, Jacobian* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t w = pl.W; w-- > 0;) {
+        for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);
+        XYZZ s = ld_xyzz(grpW + (uint64_t)w * pl.G);
+        xyzz_add(acc, s);
+    }
+    *out = xyzz_to_jacobian_normalized(acc);
+}
+
+// ---- small helpers exposed through the ABI --------------------------------------------------------
+__global__ void g1_sum_kernel(const Jacobian* pts, uint64_t count, Jacobian* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint64_t i = 0; i < count; ++i) {
+        XYZZ p = xyzz_from_jacobian(pts[i]);
+        xyzz_add(acc, p);
+    }
+    *out = xyzz_to_jacobian_normalized(acc);
+}
+
+__global__ void __launch_bounds__(128) g1_generator_mul_kernel(const Fr* scalars, uint64_t n, Affine* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = scalars[i].from_mont();
+    Fq gx = Fq::one(), gy = Fq::one().dbl();  // generator (1, 2)
+    XYZZ acc = XYZZ::identity();
+    for (int limb = 7; limb >= 0; --limb)
+        for (int b = 31; b >= 0; --b) {
+            acc = xyzz_dbl(acc);
+            if ((s.l.v[limb] >> b) & 1) xyzz_madd(acc, gx, gy);
+        }
+    out[i] = xyzz_to_affine(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+static uint32_t pick_window(uint64_t n) {
+    if (n < 32) return n < 4 ? 2 : 4;
+    double best = 1e300;
+    uint32_t bc = 8;
+    for (uint32_t c = 5; c <= 23; ++c) {
+        uint32_t W = 254 / c + 1;
+        if ((double)n * W >= 4.0e9) continue;  // sorted-entry positions are 32-bit
+        double cost = (double)n * W * 10.0 + (double)W * (double)(1ull << c) * 16.0 + (double)W * 4096.0;
+        if (cost < best) {
+            best = cost;
+            bc = c;
+        }
+    }
+    return bc;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev) {
+    if (n >= (1ull << 31)) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n = %llu >= 2^31", (unsigned long long)n);
+    MsmPlan pl;
+    pl.c = ctx->msm_window ? ctx->msm_window : pick_window(n);
+    if (pl.c < 2 || pl.c > 24) return fail(ctx, B200ZK_E_INVALID, "msm: window %u out of range [2,24]", pl.c);
+    pl.W = 254 / pl.c + 1;
+    pl.B = 1u << (pl.c - 1);
+    pl.NB = (uint64_t)pl.W * pl.B;
+    pl.g = pl.B < (uint32_t)GROUP ? pl.B : (uint32_t)GROUP;
+    pl.G = pl.B / pl.g;
+    uint32_t log_g = 0;
+    while ((1u << log_g) < pl.g) ++log_g;
+    uint64_t max_entries = n * pl.W;
+    if (max_entries >= 0xffffffffull) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n*W too large for window %u", pl.c);
+    ctx->last_c = pl.c;
+    ctx->last_windows = pl.W;
+    ctx->last_adds = max_entries;
+
+    uint64_t nthreads = (max_entries + ACC_L - 1) / ACC_L;
+    if (nthreads == 0) nthreads = 1;
+    uint32_t ntiles = (uint32_t)((pl.NB + SCAN_TILE - 1) / SCAN_TILE);
+    // carve the scratch arena
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_hist = carve(4 * (pl.NB + 1)), o_offs = carve(4 * (pl.NB + 1)), o_cursor = carve(4 * (pl.NB + 1));
+    size_t o_tiles = carve(4 * (size_t)(ntiles + 1));
+    size_t o_entries = carve(4 * (max_entries + 4));
+    size_t o_buckets = carve(sizeof(XYZZ) * pl.NB);
+    size_t o_pid = carve(4 * 2 * nthreads), o_pval = carve(sizeof(XYZZ) * 2 * nthreads);
+    size_t o_gr = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G), o_gw = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G);
+    B2_TRY(scratch_reserve(ctx, ctx->msm_work, off));
+    char* base = (char*)ctx->msm_work.p;
+    uint32_t* hist = (uint32_t*)(base + o_hist);
+    uint32_t* offsets = (uint32_t*)(base + o_offs);
+    uint32_t* cursor = (uint32_t*)(base + o_cursor);
+    uint32_t* tiles = (uint32_t*)(base + o_tiles);
+    uint32_t* entries = (uint32_t*)(base + o_entries);
+    XYZZ* buckets = (XYZZ*)(base + o_buckets);
+    uint32_t* pid = (uint32_t*)(base + o_pid);
+    XYZZ* pval = (XYZZ*)(base + o_pval);
+    XYZZ* grpR = (XYZZ*)(base + o_gr);
+    XYZZ* grpW = (XYZZ*)(base + o_gw);
+
+    cudaStream_t st = ctx->stream;
+    B2_CUDA(ctx, cudaMemsetAsync(hist, 0, 4 * (pl.NB + 1), st));
+    B2_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * pl.NB, st));
+    uint32_t sblocks = (uint32_t)ctx->sm_count * 8;
+    if (n) {
+        uint64_t want = (n + 255) / 256;
+        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
+        msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    scan_tile_sums<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles);
+    B2_LAUNCH_CHECK(ctx);
+    scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB);
+    B2_LAUNCH_CHECK(ctx);
+    scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles, offsets, cursor);
+    B2_LAUNCH_CHECK(ctx);
+    if (n) {
+        uint64_t want = (n + 255) / 256;
+        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
+        msm_scatter<<<blocks, 256, 0, st>>>(scalars, n, pl, cursor, entries);
+        B2_LAUNCH_CHECK(ctx);
+        uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
+        msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads);
+        B2_LAUNCH_CHECK(ctx);
+        uint64_t nrec = 2 * nthreads;
+        msm_combine<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(pid, pval, nrec, buckets);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    {
+        uint64_t total = (uint64_t)pl.W * pl.G;
+        msm_group_reduce<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(buckets, pl, grpR, grpW);
+        B2_LAUNCH_CHECK(ctx);
+        for (uint32_t level = 0; (pl.G >> level) > 1; ++level) {
+            uint64_t t2 = (uint64_t)pl.W * (pl.G >> (level + 1));
+            msm_tree_level<<<(uint32_t)((t2 + 127) / 128), 128, 0, st>>>(pl, level, log_g, grpR, grpW);
+            B2_LAUNCH_CHECK(ctx);
+        }
+        msm_finish<<<1, 32, 0, st>>>(pl, grpW, out_dev);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    return B200ZK_OK;
+}
+
+int32_t g1_sum_run(b200zk_ctx* ctx, const Jacobian* pts, uint64_t count, Jacobian* out_dev) {
+    g1_sum_kernel<<<1, 32, 0, ctx->stream>>>(pts, count, out_dev);
+    B2_LAUNCH_CHECK(ctx);
+    return B200ZK_OK;
+}
+
+int32_t g1_generator_mul_run(b200zk_ctx* ctx, const Fr* scalars, uint64_t n, Affine* out) {
+    if (!n) return B200ZK_OK;
+    g1_generator_mul_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(scalars, n, out);
+    B2_LAUNCH_CHECK(ctx);
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

@@ -25,3 +25,27 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def load_pkg():
+    """The product package lives in `scroll-prover_b200/` (hyphenated, as the layout requires)."""
+    import importlib
+
+    name = "scroll-prover_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    mod = importlib.import_module(name)
+    sys.modules.setdefault("scroll_prover_b200", mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def zk():
+    return load_pkg()
+
+
+@pytest.fixture(scope="session")
+def ctx(zk):
+    c = zk.Context(0)
+    yield c
+    c.close()

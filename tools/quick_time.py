@@ -1,0 +1,71 @@
+"""Quick device timing of the hot kernels (development aid; bench.py is the judged harness)."""
+import importlib
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+zk = importlib.import_module("scroll-prover_b200")
+
+R = zk.R_MOD
+
+
+def rand_fr(n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = torch.randint(-(2**63), 2**63 - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+    t[:, 3] &= 0x0FFFFFFFFFFFFFFF  # < 2^252 < r: valid Montgomery limbs
+    return t
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ctx = zk.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    out = []
+    for log_n in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "16,20,22,24").split(",")]:
+        n = 1 << log_n
+        a = rand_fr(n, log_n)
+        w = zk.fr_from_int(pow(zk._ROOT_OF_UNITY, 1 << (28 - log_n), R))
+        best, med = timeit(lambda: ctx.best_fft(a, w, log_n))
+        bf = n / 2 * log_n
+        out.append({"op": "ntt", "log_n": log_n, "ms_best": best, "ms_med": med, "Gbutterflies_s": bf / best / 1e6})
+        print(json.dumps(out[-1]), flush=True)
+    for log_n in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "16,20,22").split(",")]:
+        n = 1 << log_n
+        s = rand_fr(n, 100 + log_n)
+        g = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        t0 = time.time()
+        ctx.g1_generator_mul_batch(s, out=g)
+        torch.cuda.synchronize()
+        gen_s = time.time() - t0
+        srs = ctx.srs_register(g)
+        sc = rand_fr(n, 200 + log_n)
+        best, med = timeit(lambda: srs.msm(sc), reps=3, warm=1)
+        st = ctx.msm_last_stats()
+        out.append({"op": "msm", "log_n": log_n, "ms_best": best, "ms_med": med, "c": st["window_bits"], "W": st["n_windows"],
+                    "Gadds_s": n * st["n_windows"] / best / 1e6, "Mpoints_s": n / best / 1e3, "srs_gen_s": gen_s})
+        print(json.dumps(out[-1]), flush=True)
+        srs.release()
+        del g
+    json.dump(out, open("gpurun_out/quick_time.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
