@@ -123,6 +123,11 @@ B200ZK_API int32_t b200zk_kate_division(b200zk_ctx* ctx, void* q, const void* a,
 /* element-wise Fr/Fq Montgomery product of two arrays on the device (field-layer parity tests) */
 B200ZK_API int32_t b200zk_debug_field_op(b200zk_ctx* ctx, int field /*0 Fr,1 Fq*/, int op /*0 mul,1 add,2 sub,3 inv*/,
                               void* r, const void* a, const void* b, uint64_t n);
+/* Per-kernel-class device timing with CUDA events on the context stream (bench.py's roofline):
+ * classes: ntt_pass ntt_table msm_count msm_scan msm_scatter msm_accumulate msm_combine msm_reduce msm_finish poly */
+B200ZK_API int32_t b200zk_profile_enable(b200zk_ctx* ctx, int on);
+B200ZK_API int32_t b200zk_profile_reset(b200zk_ctx* ctx);
+B200ZK_API int32_t b200zk_profile_read(b200zk_ctx* ctx, const char* kernel_class, double* total_ms, uint64_t* count);
 /* MSM tuning knobs (window bits; 0 = auto) and last-call statistics, for bench/roofline reporting */
 B200ZK_API int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c);
 B200ZK_API int32_t b200zk_msm_last_stats(const b200zk_ctx* ctx, uint32_t* window_bits, uint32_t* n_windows, uint64_t* n_bucket_adds);

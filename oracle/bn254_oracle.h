@@ -108,6 +108,7 @@ void halo2_commit(const g1_affine_t *bases, const fr_t *poly, uint64_t n, int th
 /* ---- deterministic test-vector generator shared with the GPU tests (xorshift64*) ---- */
 void oracle_fill_fr(fr_t *out, uint64_t n, uint64_t seed, int witness_like);
 void oracle_fill_points(g1_affine_t *out, uint64_t n, uint64_t seed, int threads);
+void oracle_fill_points_chain(g1_affine_t *out, uint64_t n, uint64_t seed, int threads);
 
 #ifdef __cplusplus
 }

@@ -346,3 +346,50 @@ void oracle_fill_points(g1_affine_t *out, uint64_t n, uint64_t seed, int threads
     free(jobs);
     free(tids);
 }
+
+/* Fast bulk generator of distinct valid curve points for the large CPU-baseline runs:
+ * thread chunk [lo,hi): P_lo = s_lo*G, P_{i+1} = P_i + D with one fixed D; batch-normalised. */
+typedef struct {
+    g1_affine_t *out;
+    uint64_t lo, hi, seed;
+} chain_job_t;
+
+static void *chain_worker(void *arg) {
+    chain_job_t *j = (chain_job_t *)arg;
+    g1_affine_t gen, D;
+    g1_generator(&gen);
+    g1_t G, P, Dj;
+    g1_from_affine(&G, &gen);
+    fr_t s;
+    oracle_fill_fr(&s, 1, j->seed ^ 0xD1FFD1FFULL, 0);
+    g1_mul(&Dj, &G, &s);
+    g1_to_affine(&D, &Dj);
+    oracle_fill_fr(&s, 1, j->seed * 0x9E3779B97F4A7C15ULL + j->lo + 1, 0);
+    g1_mul(&P, &G, &s);
+    const uint64_t BATCH = 4096;
+    g1_t *tmp = (g1_t *)malloc(sizeof(g1_t) * BATCH);
+    for (uint64_t i = j->lo; i < j->hi; i += BATCH) {
+        uint64_t cnt = (j->hi - i < BATCH) ? j->hi - i : BATCH;
+        for (uint64_t t = 0; t < cnt; ++t) {
+            tmp[t] = P;
+            g1_add_mixed(&P, &P, &D);
+        }
+        g1_batch_normalize(j->out + i, tmp, cnt);
+    }
+    free(tmp);
+    return NULL;
+}
+
+void oracle_fill_points_chain(g1_affine_t *out, uint64_t n, uint64_t seed, int threads) {
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+    chain_job_t *jobs = (chain_job_t *)malloc(sizeof(chain_job_t) * threads);
+    pthread_t *tids = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = (chain_job_t){out, n * t / threads, n * (t + 1) / threads, seed};
+        pthread_create(&tids[t], NULL, chain_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(tids[t], NULL);
+    free(jobs);
+    free(tids);
+}

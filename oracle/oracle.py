@@ -396,3 +396,10 @@ def fill_points(n: int, seed: int, threads: int = 8) -> np.ndarray:
     out = np.zeros((n, 8), np.uint64)
     lib.oracle_fill_points(_p(out), C.c_uint64(n), C.c_uint64(seed), C.c_int(threads))
     return out
+
+
+def fill_points_chain(n: int, seed: int, threads: int = 8) -> np.ndarray:
+    """distinct valid points P_0 + i*D, cheap to generate at 2^24+ (CPU-baseline inputs only)"""
+    out = np.zeros((n, 8), np.uint64)
+    lib.oracle_fill_points_chain(_p(out), C.c_uint64(n), C.c_uint64(seed), C.c_int(threads))
+    return out

@@ -85,6 +85,9 @@ def _load():
         "b200zk_batch_invert": [vp, vp, u64],
         "b200zk_kate_division": [vp, vp, vp, u64, vp],
         "b200zk_debug_field_op": [vp, C.c_int, C.c_int, vp, vp, vp, u64],
+        "b200zk_profile_enable": [vp, C.c_int],
+        "b200zk_profile_reset": [vp],
+        "b200zk_profile_read": [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)],
         "b200zk_msm_set_window": [vp, u32],
         "b200zk_msm_last_stats": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
     }
@@ -103,7 +106,7 @@ ABI_SYMBOLS = [
     "b200zk_srs_register", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
-    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_msm_set_window", "b200zk_msm_last_stats",
+    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats",
 ]
 
 _lib = None
@@ -178,6 +181,23 @@ class Context:
         v = C.c_uint64()
         self._ck(lib().b200zk_ctx_launch_count(self._h, C.byref(v)))
         return v.value
+
+    PROFILE_CLASSES = ("ntt_pass", "ntt_table", "msm_count", "msm_scan", "msm_scatter", "msm_accumulate", "msm_combine",
+                       "msm_reduce", "msm_finish", "poly")
+
+    def profile_enable(self, on: bool = True):
+        self._ck(lib().b200zk_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._ck(lib().b200zk_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        out = {}
+        for name in self.PROFILE_CLASSES:
+            ms, cnt = C.c_double(), C.c_uint64()
+            self._ck(lib().b200zk_profile_read(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
+            out[name] = {"ms": ms.value, "count": cnt.value}
+        return out
 
     # ---- SRS / MSM
     def srs_register(self, bases, tag: int = SRS_G) -> "Srs":

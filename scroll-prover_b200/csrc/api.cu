@@ -390,6 +390,38 @@ int32_t b200zk_debug_field_op(b200zk_ctx* ctx, int field, int op, void* r, const
     return deliver(ctx, r, ctx->stage_out.p, bytes);
 }
 
+int32_t b200zk_profile_enable(b200zk_ctx* ctx, int on) {
+    CHECK_CTX(ctx);
+    Guard g(ctx);
+    ctx->profiling = on != 0;
+    return B200ZK_OK;
+}
+int32_t b200zk_profile_reset(b200zk_ctx* ctx) {
+    CHECK_CTX(ctx);
+    Guard g(ctx);
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_resolve(ctx);
+    for (int i = 0; i < PROF_NKEYS; ++i) {
+        ctx->prof_ms[i] = 0;
+        ctx->prof_cnt[i] = 0;
+    }
+    return B200ZK_OK;
+}
+int32_t b200zk_profile_read(b200zk_ctx* ctx, const char* name, double* total_ms, uint64_t* count) {
+    CHECK_CTX(ctx);
+    if (!name) return fail(ctx, B200ZK_E_INVALID, "profile_read: null name");
+    Guard g(ctx);
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_resolve(ctx);
+    for (int i = 0; i < PROF_NKEYS; ++i)
+        if (strcmp(name, PROF_NAMES[i]) == 0) {
+            if (total_ms) *total_ms = ctx->prof_ms[i];
+            if (count) *count = ctx->prof_cnt[i];
+            return B200ZK_OK;
+        }
+    return fail(ctx, B200ZK_E_INVALID, "profile_read: unknown kernel class '%s'", name);
+}
+
 int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c) {
     CHECK_CTX(ctx);
     if (c != 0 && (c < 2 || c > 24)) return fail(ctx, B200ZK_E_INVALID, "msm window %u out of range", c);

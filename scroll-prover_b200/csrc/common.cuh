@@ -21,6 +21,16 @@ struct TwiddleTable {  // universal per-stage twiddles for one root: tab[2^(u-1)
     Fr* dev;
 };
 
+// per-kernel-class device timing (CUDA events on the context stream), read by bench.py for the roofline
+enum ProfKey { PROF_NTT_PASS = 0, PROF_NTT_TABLE, PROF_MSM_COUNT, PROF_MSM_SCAN, PROF_MSM_SCATTER, PROF_MSM_ACCUM,
+               PROF_MSM_COMBINE, PROF_MSM_REDUCE, PROF_MSM_FINISH, PROF_POLY, PROF_NKEYS };
+static const char* const PROF_NAMES[PROF_NKEYS] = {"ntt_pass", "ntt_table", "msm_count", "msm_scan", "msm_scatter",
+                                                   "msm_accumulate", "msm_combine", "msm_reduce", "msm_finish", "poly"};
+struct ProfSpan {
+    int key;
+    cudaEvent_t e0, e1;
+};
+
 struct Scratch {  // grow-only device allocation
     void* p = nullptr;
     size_t cap = 0;
@@ -48,6 +58,12 @@ struct b200zk_ctx {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<b200zk::TwiddleTable> tables;
+    // profiling
+    bool profiling = false;
+    std::vector<b200zk::ProfSpan> prof_open;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[b200zk::PROF_NKEYS] = {0};
+    uint64_t prof_cnt[b200zk::PROF_NKEYS] = {0};
     // msm knobs / stats
     uint32_t msm_window = 0;
     uint32_t last_c = 0, last_windows = 0;
@@ -85,6 +101,47 @@ inline int32_t fail(b200zk_ctx* ctx, int32_t code, const char* fmt, ...) {
         (ctx)->launches++;                   \
         B2_CUDA(ctx, cudaGetLastError());    \
     } while (0)
+
+inline cudaEvent_t prof_event(b200zk_ctx* ctx) {
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// usage: ProfScope ps(ctx, PROF_X); ...launches...   (records on the context stream when profiling is on)
+struct ProfScope {
+    b200zk_ctx* ctx;
+    ProfSpan sp;
+    bool on;
+    ProfScope(b200zk_ctx* c, int key) : ctx(c), on(c->profiling) {
+        if (!on) return;
+        sp.key = key;
+        sp.e0 = prof_event(c);
+        sp.e1 = prof_event(c);
+        cudaEventRecord(sp.e0, c->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(sp.e1, ctx->stream);
+        ctx->prof_open.push_back(sp);
+    }
+};
+inline void prof_resolve(b200zk_ctx* ctx) {
+    for (auto& sp : ctx->prof_open) {
+        float ms = 0;
+        if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+            ctx->prof_ms[sp.key] += ms;
+            ctx->prof_cnt[sp.key] += 1;
+        }
+        ctx->prof_pool.push_back(sp.e0);
+        ctx->prof_pool.push_back(sp.e1);
+    }
+    ctx->prof_open.clear();
+}
 
 inline int32_t scratch_reserve(b200zk_ctx* ctx, Scratch& s, size_t bytes) {
     if (bytes <= s.cap) return B200ZK_OK;

@@ -402,28 +402,44 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     if (n) {
         uint64_t want = (n + 255) / 256;
         uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
-        msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist);
-        B2_LAUNCH_CHECK(ctx);
-    }
-    scan_tile_sums<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles);
-    B2_LAUNCH_CHECK(ctx);
-    scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB);
-    B2_LAUNCH_CHECK(ctx);
-    scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles, offsets, cursor);
-    B2_LAUNCH_CHECK(ctx);
-    if (n) {
-        uint64_t want = (n + 255) / 256;
-        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
-        msm_scatter<<<blocks, 256, 0, st>>>(scalars, n, pl, cursor, entries);
-        B2_LAUNCH_CHECK(ctx);
-        uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
-        msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads);
-        B2_LAUNCH_CHECK(ctx);
-        uint64_t nrec = 2 * nthreads;
-        msm_combine<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(pid, pval, nrec, buckets);
+        {
+            ProfScope ps_(ctx, PROF_MSM_COUNT);
+            msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist);
+        }
         B2_LAUNCH_CHECK(ctx);
     }
     {
+        ProfScope ps_(ctx, PROF_MSM_SCAN);
+        scan_tile_sums<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles);
+        B2_LAUNCH_CHECK(ctx);
+        scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB);
+        B2_LAUNCH_CHECK(ctx);
+        scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles, offsets, cursor);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    if (n) {
+        uint64_t want = (n + 255) / 256;
+        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
+        {
+            ProfScope ps_(ctx, PROF_MSM_SCATTER);
+            msm_scatter<<<blocks, 256, 0, st>>>(scalars, n, pl, cursor, entries);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
+        {
+            ProfScope ps_(ctx, PROF_MSM_ACCUM);
+            msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        uint64_t nrec = 2 * nthreads;
+        {
+            ProfScope ps_(ctx, PROF_MSM_COMBINE);
+            msm_combine<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(pid, pval, nrec, buckets);
+        }
+        B2_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope ps_(ctx, PROF_MSM_REDUCE);
         uint64_t total = (uint64_t)pl.W * pl.G;
         msm_group_reduce<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(buckets, pl, grpR, grpW);
         B2_LAUNCH_CHECK(ctx);

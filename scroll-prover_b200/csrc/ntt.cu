@@ -296,7 +296,10 @@ static int32_t get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const
     uint64_t total = 1ull << log_n;
     uint32_t tpb = 256;
     uint32_t blocks = (uint32_t)((total + tpb - 1) / tpb);
-    ntt_build_table<<<blocks, tpb, 0, ctx->stream>>>(dev, roots, log_n);
+    {
+        ProfScope ps(ctx, PROF_NTT_TABLE);
+        ntt_build_table<<<blocks, tpb, 0, ctx->stream>>>(dev, roots, log_n);
+    }
     B2_LAUNCH_CHECK(ctx);
     ctx->tables.push_back({omega, log_n, dev});
     *out = dev;
@@ -330,7 +333,10 @@ static int32_t launch_pass(b200zk_ctx* ctx, const Fr* in, Fr* out, const Fr* tab
     uint64_t tiles = (1ull << ps.log_n) / E;
     uint32_t nb = (L >> 1) * C;
     uint32_t threads = nb >= NTT_THREADS ? NTT_THREADS : (nb < 32 ? 32 : nb);
-    ntt_pass_kernel<C, LAST><<<(uint32_t)tiles, threads, smem, ctx->stream>>>(in, out, tab, ps, pre_c, post_c);
+    {
+        ProfScope psc(ctx, PROF_NTT_PASS);
+        ntt_pass_kernel<C, LAST><<<(uint32_t)tiles, threads, smem, ctx->stream>>>(in, out, tab, ps, pre_c, post_c);
+    }
     B2_LAUNCH_CHECK(ctx);
     return B200ZK_OK;
 }

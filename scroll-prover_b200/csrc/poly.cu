@@ -49,6 +49,7 @@ static uint32_t ew_blocks(b200zk_ctx* ctx, uint64_t n) {
 int32_t poly_ew(b200zk_ctx* ctx, int op, Fr* r, const Fr* a, const Fr* b, const Fr& s, uint64_t n) {
     if (n == 0) return B200ZK_OK;
     uint32_t blocks = ew_blocks(ctx, n);
+    ProfScope ps_(ctx, PROF_POLY);
     switch (op) {
         case OP_ADD: poly_ew_kernel<OP_ADD><<<blocks, 256, 0, ctx->stream>>>(r, a, b, s, n); break;
         case OP_SUB: poly_ew_kernel<OP_SUB><<<blocks, 256, 0, ctx->stream>>>(r, a, b, s, n); break;

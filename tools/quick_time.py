@@ -37,15 +37,19 @@ def timeit(fn, reps=5, warm=2):
 
 def main():
     ctx = zk.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)  # a non-default stream so that the library launches where our events are
+    ctx.set_stream(stream.cuda_stream)
     out = []
     for log_n in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "16,20,22,24").split(",")]:
         n = 1 << log_n
         a = rand_fr(n, log_n)
         w = zk.fr_from_int(pow(zk._ROOT_OF_UNITY, 1 << (28 - log_n), R))
         best, med = timeit(lambda: ctx.best_fft(a, w, log_n))
+        ctx.profile_enable(True); ctx.profile_reset(); ctx.best_fft(a, w, log_n); prof = ctx.profile_read(); ctx.profile_enable(False)
         bf = n / 2 * log_n
-        out.append({"op": "ntt", "log_n": log_n, "ms_best": best, "ms_med": med, "Gbutterflies_s": bf / best / 1e6})
+        out.append({"op": "ntt", "log_n": log_n, "ms_best": best, "ms_med": med, "Gbutterflies_s": bf / best / 1e6,
+                    "prof": {k: round(v["ms"], 4) for k, v in prof.items() if v["count"]}})
         print(json.dumps(out[-1]), flush=True)
     for log_n in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "16,20,22").split(",")]:
         n = 1 << log_n
@@ -59,8 +63,10 @@ def main():
         sc = rand_fr(n, 200 + log_n)
         best, med = timeit(lambda: srs.msm(sc), reps=3, warm=1)
         st = ctx.msm_last_stats()
+        ctx.profile_enable(True); ctx.profile_reset(); srs.msm(sc); prof = ctx.profile_read(); ctx.profile_enable(False)
         out.append({"op": "msm", "log_n": log_n, "ms_best": best, "ms_med": med, "c": st["window_bits"], "W": st["n_windows"],
-                    "Gadds_s": n * st["n_windows"] / best / 1e6, "Mpoints_s": n / best / 1e3, "srs_gen_s": gen_s})
+                    "Gadds_s": n * st["n_windows"] / best / 1e6, "Mpoints_s": n / best / 1e3, "srs_gen_s": gen_s,
+                    "prof": {k: round(v["ms"], 4) for k, v in prof.items() if v["count"]}})
         print(json.dumps(out[-1]), flush=True)
         srs.release()
         del g
