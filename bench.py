@@ -320,7 +320,10 @@ def run_b200(args):
         sampler.start()
     sec, wall, prof, launches = timed(step_resident, args.steps, args.warmup, profile=True)
     clocks = sampler.stop() if sampler else None
-    e2e_sec, e2e_wall, _, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+    if args.skip_e2e:
+        e2e_sec = None
+    else:
+        e2e_sec, e2e_wall, _, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
 
     # ---- units processed (whole job) for the throughput figures
     st = ctx.msm_last_stats()
@@ -394,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=24, help="log2 rows of the proved layer (24 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident arm only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
