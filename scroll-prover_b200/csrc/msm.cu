@@ -28,6 +28,7 @@ static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
 static constexpr int ACC_L = 64;        // sorted entries per accumulate thread
 static constexpr int GROUP = 32;        // buckets per first-level reduction group
+static constexpr uint32_t BIG_BUCKET = 4 * ACC_L;  // buckets above this size are split over threads
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -44,49 +45,54 @@ __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
     y.l.v[4] = d.x; y.l.v[5] = d.y; y.l.v[6] = d.z; y.l.v[7] = d.w;
 }
 
-// signed-digit walk over the canonical scalar; f(w, magnitude, negative) for every non-zero digit
-template <class FN>
-__device__ __forceinline__ void for_each_digit(const Fr& s_mont, uint32_t c, uint32_t W, FN f) {
-    Fr s = s_mont.from_mont();
-    uint32_t l[8];
+// every scalar once: canonical form, signed digits -> digits[w*n + i] (magnitude | sign<<31, 0 = skip) + histogram
+__global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* hist, uint32_t* digits) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr s = scalars[i];
+        if (s.is_zero()) {
+            for (uint32_t w = 0; w < pl.W; ++w) digits[(uint64_t)w * n + i] = 0;
+            continue;
+        }
+        s = s.from_mont();
+        uint32_t l[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) l[i] = s.l.v[i];
-    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < W; ++w) {
-        uint32_t v = (l[0] & mask) + carry;
+        for (int k = 0; k < 8; ++k) l[k] = s.l.v[k];
+        const uint32_t c = pl.c, mask = (1u << c) - 1, half = 1u << (c - 1);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < pl.W; ++w) {
+            uint32_t v = (l[0] & mask) + carry;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) l[i] = __funnelshift_r(l[i], l[i + 1], c);
-        l[7] >>= c;
-        if (v > half) {
-            uint32_t mag = (1u << c) - v;
-            carry = 1;
-            if (mag) f(w, mag, true);
-        } else {
-            carry = 0;
-            if (v) f(w, v, false);
+            for (int k = 0; k < 7; ++k) l[k] = __funnelshift_r(l[k], l[k + 1], c);
+            l[7] >>= c;
+            uint32_t enc;
+            if (v > half) {
+                enc = (1u << c) - v;  // magnitude of the negative digit (0 when v == 2^c)
+                carry = 1;
+                if (enc) enc |= 0x80000000u;
+            } else {
+                enc = v;
+                carry = 0;
+            }
+            digits[(uint64_t)w * n + i] = enc;
+            if (enc) atomicAdd(&hist[(uint64_t)w * pl.B + (enc & 0x7fffffffu) - 1], 1u);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* hist) {
+// counting-sort scatter in WINDOW-MAJOR order: concurrently running blocks work on the same window, so the
+// random 4-byte stores fall into one n*4-byte region that stays L2-resident (64 MiB at n = 2^24)
+__global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ digits, uint64_t n, MsmPlan pl,
+                                                   uint32_t* cursor, uint32_t* entries) {
+    uint64_t total = n * pl.W;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Fr s = scalars[i];
-        if (s.is_zero()) continue;
-        for_each_digit(s, pl.c, pl.W, [&](uint32_t w, uint32_t mag, bool) { atomicAdd(&hist[(uint64_t)w * pl.B + mag - 1], 1u); });
-    }
-}
-
-__global__ void __launch_bounds__(256) msm_scatter(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* cursor, uint32_t* entries) {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Fr s = scalars[i];
-        if (s.is_zero()) continue;
-        for_each_digit(s, pl.c, pl.W, [&](uint32_t w, uint32_t mag, bool neg) {
-            uint32_t pos = atomicAdd(&cursor[(uint64_t)w * pl.B + mag - 1], 1u);
-            entries[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
-        });
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        uint32_t d = digits[idx];
+        if (!d) continue;
+        uint64_t w = idx / n;
+        uint32_t i = (uint32_t)(idx - w * n);
+        uint32_t pos = atomicAdd(&cursor[w * pl.B + (d & 0x7fffffffu) - 1], 1u);
+        entries[pos] = i | (d & 0x80000000u);
     }
 }
 
@@ -185,7 +191,23 @@ __device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
     return v;
 }
 
-// offsets has NB + 1 entries (offsets[NB] = total number of sorted entries M).
+__device__ __forceinline__ void accumulate_range(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries,
+                                                 uint32_t a0, uint32_t a1, XYZZ& acc) {
+    for (uint32_t pos = a0; pos < a1; ++pos) {
+        uint32_t e = entries[pos];
+        Fq px, py;
+        ld_affine(bases + (e & 0x7fffffffu), px, py);
+        if (px.is_zero() && py.is_zero()) continue;  // identity base
+        if (e & 0x80000000u) py = py.neg();
+        xyzz_madd(acc, px, py);
+    }
+}
+
+// offsets has NB + 1 entries (offsets[NB] = M sorted entries).  Thread tau has the nominal entry range
+// [tau*L, (tau+1)*L).  It OWNS every bucket of at most BIG entries that STARTS in its range (summed whole and
+// stored directly: no partials for ordinary buckets), and for buckets larger than BIG it sums only the overlap
+// with its range and emits a partial record (<= 2 per thread) that msm_combine_* merge -- so a bucket holding
+// millions of equal digits (typical witness columns) is still spread over thousands of threads.
 __global__ void __launch_bounds__(256, 2)
 msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                uint64_t NB, XYZZ* __restrict__ buckets, uint32_t* __restrict__ part_id, XYZZ* __restrict__ part_val,
@@ -197,50 +219,86 @@ msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ en
     part_id[2 * tau] = PART_INVALID;
     part_id[2 * tau + 1] = PART_INVALID;
     if (start >= M) return;
-    uint32_t end = (start + ACC_L < M) ? (uint32_t)(start + ACC_L) : M;
-    // largest b with offsets[b] <= start
-    uint64_t lo = 0, hi = NB;  // invariant: offsets[lo] <= start, offsets[hi] > start  (offsets[NB] = M > start)
+    const uint32_t lo_e = (uint32_t)start;
+    const uint32_t hi_e = (start + ACC_L < M) ? (uint32_t)(start + ACC_L) : M;
+    // largest b with offsets[b] <= lo_e  (the non-empty bucket containing entry lo_e)
+    uint64_t lo = 0, hi = NB;
     while (hi - lo > 1) {
         uint64_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= start) lo = mid; else hi = mid;
+        if (offsets[mid] <= lo_e) lo = mid; else hi = mid;
     }
-    uint32_t b = (uint32_t)lo;
-    uint32_t bucket_end = offsets[b + 1];
-    bool run_starts = (offsets[b] == (uint32_t)start);
-    bool first_run = true;
-    XYZZ acc = XYZZ::identity();
-    uint32_t pos = (uint32_t)start;
+    uint64_t b = lo;
+    uint32_t s_b = offsets[b];
+    uint32_t slot = 0;
     while (true) {
-        bool at_end = (pos == end);
-        if (at_end || pos == bucket_end) {
-            bool run_ends = (pos == bucket_end);
-            if (run_starts && run_ends) {
-                st_xyzz(buckets + b, acc);
-            } else {
-                uint32_t slot = first_run ? 0 : 1;
-                part_id[2 * tau + slot] = b | (run_starts ? PART_STARTS : 0u) | (run_ends ? PART_ENDS : 0u);
-                st_xyzz(part_val + 2 * tau + slot, acc);
-            }
-            if (at_end) break;
-            first_run = false;
-            acc = XYZZ::identity();
-            do { ++b; bucket_end = offsets[b + 1]; } while (bucket_end == pos);  // skip empty buckets
-            run_starts = true;
+        uint32_t e_b = offsets[b + 1];
+        uint32_t size = e_b - s_b;
+        if (size > BIG_BUCKET) {
+            uint32_t a0 = s_b > lo_e ? s_b : lo_e, a1 = e_b < hi_e ? e_b : hi_e;
+            XYZZ acc = XYZZ::identity();
+            accumulate_range(bases, entries, a0, a1, acc);
+            part_id[2 * tau + slot] = (uint32_t)b | (a0 == s_b ? PART_STARTS : 0u) | (a1 == e_b ? PART_ENDS : 0u);
+            st_xyzz(part_val + 2 * tau + slot, acc);
+            ++slot;
+        } else if (size && s_b >= lo_e) {
+            XYZZ acc = XYZZ::identity();
+            accumulate_range(bases, entries, s_b, e_b, acc);
+            st_xyzz(buckets + b, acc);
         }
-        uint32_t e = entries[pos];
-        Fq px, py;
-        ld_affine(bases + (e & 0x7fffffffu), px, py);
-        if (!(px.is_zero() && py.is_zero())) {
-            if (e & 0x80000000u) py = py.neg();
-            xyzz_madd(acc, px, py);
-        }
-        ++pos;
+        ++b;
+        s_b = e_b;
+        if (b >= NB || s_b >= hi_e) break;
     }
 }
 
-// head record of every straddling bucket sums the records up to the one that ends the bucket
-__global__ void __launch_bounds__(128) msm_combine(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
-                                                   uint64_t nrec, XYZZ* __restrict__ buckets) {
+// One level of the partial-record reduction: thread sigma scans LR consecutive records (sorted by bucket, invalid
+// slots skipped), sums runs of equal bucket id; a run that saw both the STARTS and the ENDS record is complete and
+// is stored to its bucket, otherwise it is re-emitted (<= 2 per thread) for the next level.
+static constexpr int COMBINE_LR = 64;
+__global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restrict__ in_id, const XYZZ* __restrict__ in_val,
+                                                         uint64_t nrec, XYZZ* __restrict__ buckets, uint32_t* __restrict__ out_id,
+                                                         XYZZ* __restrict__ out_val, uint64_t nthreads) {
+    uint64_t sigma = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sigma >= nthreads) return;
+    out_id[2 * sigma] = PART_INVALID;
+    out_id[2 * sigma + 1] = PART_INVALID;
+    uint64_t r0 = sigma * COMBINE_LR, r1 = r0 + COMBINE_LR;
+    if (r1 > nrec) r1 = nrec;
+    bool have = false;
+    uint32_t cur = 0, flags = 0, slot = 0;
+    XYZZ acc = XYZZ::identity();
+    auto flush = [&]() {
+        if (!have) return;
+        if ((flags & PART_STARTS) && (flags & PART_ENDS)) {
+            st_xyzz(buckets + cur, acc);
+        } else {
+            out_id[2 * sigma + slot] = cur | flags;
+            st_xyzz(out_val + 2 * sigma + slot, acc);
+            ++slot;
+        }
+    };
+    for (uint64_t r = r0; r < r1; ++r) {
+        uint32_t id = in_id[r];
+        if ((id & PART_INVALID) == PART_INVALID) continue;
+        uint32_t bkt = id & PART_INVALID;
+        if (!have || bkt != cur) {
+            flush();
+            have = true;
+            cur = bkt;
+            flags = id & (PART_STARTS | PART_ENDS);
+            acc = ld_xyzz(in_val + r);
+        } else {
+            flags |= id & (PART_STARTS | PART_ENDS);
+            XYZZ v = ld_xyzz(in_val + r);
+            xyzz_add(acc, v);
+        }
+    }
+    flush();
+}
+
+// last level (few records): the head record of every bucket sums forward to the record that ends the bucket
+__global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
+                                                         uint64_t nrec, XYZZ* __restrict__ buckets) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
     uint32_t id = part_id[r];
@@ -379,8 +437,11 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     size_t o_hist = carve(4 * (pl.NB + 1)), o_offs = carve(4 * (pl.NB + 1)), o_cursor = carve(4 * (pl.NB + 1));
     size_t o_tiles = carve(4 * (size_t)(ntiles + 1));
     size_t o_entries = carve(4 * (max_entries + 4));
+    size_t o_digits = carve(4 * (max_entries + 4));
     size_t o_buckets = carve(sizeof(XYZZ) * pl.NB);
     size_t o_pid = carve(4 * 2 * nthreads), o_pval = carve(sizeof(XYZZ) * 2 * nthreads);
+    uint64_t nthreads2 = (2 * nthreads + COMBINE_LR - 1) / COMBINE_LR;
+    size_t o_pid2 = carve(4 * 2 * nthreads2), o_pval2 = carve(sizeof(XYZZ) * 2 * nthreads2);
     size_t o_gr = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G), o_gw = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G);
     B2_TRY(scratch_reserve(ctx, ctx->msm_work, off));
     char* base = (char*)ctx->msm_work.p;
@@ -389,6 +450,9 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     uint32_t* cursor = (uint32_t*)(base + o_cursor);
     uint32_t* tiles = (uint32_t*)(base + o_tiles);
     uint32_t* entries = (uint32_t*)(base + o_entries);
+    uint32_t* digits = (uint32_t*)(base + o_digits);
+    uint32_t* pid2 = (uint32_t*)(base + o_pid2);
+    XYZZ* pval2 = (XYZZ*)(base + o_pval2);
     XYZZ* buckets = (XYZZ*)(base + o_buckets);
     uint32_t* pid = (uint32_t*)(base + o_pid);
     XYZZ* pval = (XYZZ*)(base + o_pval);
@@ -404,7 +468,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
         {
             ProfScope ps_(ctx, PROF_MSM_COUNT);
-            msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist);
+            msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist, digits);
         }
         B2_LAUNCH_CHECK(ctx);
     }
@@ -418,11 +482,11 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         B2_LAUNCH_CHECK(ctx);
     }
     if (n) {
-        uint64_t want = (n + 255) / 256;
-        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
         {
             ProfScope ps_(ctx, PROF_MSM_SCATTER);
-            msm_scatter<<<blocks, 256, 0, st>>>(scalars, n, pl, cursor, entries);
+            uint64_t want = (max_entries + 1023) / 1024;  // 4 digits per thread, blocks issued in window-major order
+            uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
+            msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries);
         }
         B2_LAUNCH_CHECK(ctx);
         uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
@@ -431,12 +495,22 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads);
         }
         B2_LAUNCH_CHECK(ctx);
-        uint64_t nrec = 2 * nthreads;
         {
             ProfScope ps_(ctx, PROF_MSM_COMBINE);
-            msm_combine<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(pid, pval, nrec, buckets);
+            uint64_t nrec = 2 * nthreads;
+            uint32_t *in_id = pid, *out_id = pid2;
+            XYZZ *in_val = pval, *out_val = pval2;
+            while (nrec > 2048) {
+                uint64_t nt = (nrec + COMBINE_LR - 1) / COMBINE_LR;
+                msm_combine_level<<<(uint32_t)((nt + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets, out_id, out_val, nt);
+                B2_LAUNCH_CHECK(ctx);
+                nrec = 2 * nt;
+                uint32_t* ti = in_id; in_id = out_id; out_id = ti;
+                XYZZ* tv = in_val; in_val = out_val; out_val = tv;
+            }
+            msm_combine_final<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets);
+            B2_LAUNCH_CHECK(ctx);
         }
-        B2_LAUNCH_CHECK(ctx);
     }
     {
         ProfScope ps_(ctx, PROF_MSM_REDUCE);

@@ -189,6 +189,25 @@ def test_msm_heavily_skewed_buckets(ctx):
     assert not got[8:].any()  # identity: z == 0
 
 
+def test_msm_giant_bucket_is_split_and_recombined(ctx):
+    """2^18 equal scalars -> one bucket with 262144 entries: partial records go through two combine levels."""
+    import torch
+
+    n = 1 << 18
+    one = O.fr_from_int(7)
+    sc = np.tile(one, (n, 1))
+    sc[12345] = O.fr_from_int(O.R_MOD - 2)
+    tau = np.stack([O.fr_from_int(3 + i) for i in range(8)])
+    pts8 = ctx.g1_generator_mul_batch(tau)
+    bases = np.tile(pts8, (n // 8, 1))  # 8 distinct points repeated
+    got = ctx.best_multiexp(sc, bases)
+    # sum = 7 * (n/8) * sum(pts8) + (r - 2 - 7) * bases[12345]
+    G = O.g1_from_affine(O.g1_generator())
+    ssum = sum(3 + i for i in range(8))
+    k = (7 * (n // 8) * ssum + (O.R_MOD - 2 - 7) * (3 + 12345 % 8)) % O.R_MOD
+    assert np.array_equal(norm_affine(got), norm_affine(O.g1_mul(G, O.fr_from_int(k))))
+
+
 def test_msm_length_mismatch_panics_like_reference(ctx, zk):
     with pytest.raises(AssertionError):
         ctx.best_multiexp(O.fill_fr(3, 1), O.fill_points(2, 1, 1))
