@@ -130,6 +130,8 @@ B200ZK_API int32_t b200zk_profile_reset(b200zk_ctx* ctx);
 B200ZK_API int32_t b200zk_profile_read(b200zk_ctx* ctx, const char* kernel_class, double* total_ms, uint64_t* count);
 /* MSM tuning knobs (window bits; 0 = auto) and last-call statistics, for bench/roofline reporting */
 B200ZK_API int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c);
+/* bucket additions actually performed (non-zero signed digits) by all MSMs since the last reset */
+B200ZK_API int32_t b200zk_msm_total_adds(b200zk_ctx* ctx, uint64_t* actual_adds, int reset);
 B200ZK_API int32_t b200zk_msm_last_stats(const b200zk_ctx* ctx, uint32_t* window_bits, uint32_t* n_windows, uint64_t* n_bucket_adds);
 
 #ifdef __cplusplus

@@ -90,6 +90,7 @@ def _load():
         "b200zk_profile_read": [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)],
         "b200zk_msm_set_window": [vp, u32],
         "b200zk_msm_last_stats": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
+        "b200zk_msm_total_adds": [vp, C.POINTER(u64), C.c_int],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -106,7 +107,7 @@ ABI_SYMBOLS = [
     "b200zk_srs_register", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
-    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats",
+    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
 _lib = None
@@ -210,6 +211,11 @@ class Context:
         c, w, a = C.c_uint32(), C.c_uint32(), C.c_uint64()
         self._ck(lib().b200zk_msm_last_stats(self._h, C.byref(c), C.byref(w), C.byref(a)))
         return {"window_bits": c.value, "n_windows": w.value, "n_bucket_adds": a.value}
+
+    def msm_total_adds(self, reset: bool = False) -> int:
+        v = C.c_uint64()
+        self._ck(lib().b200zk_msm_total_adds(self._h, C.byref(v), int(reset)))
+        return v.value
 
     def best_multiexp(self, coeffs, bases) -> np.ndarray:
         """arithmetic::best_multiexp(coeffs, bases): panics (AssertionError) if lengths differ."""

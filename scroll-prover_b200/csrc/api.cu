@@ -68,6 +68,8 @@ int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out) {
         return B200ZK_E_CUDA;
     }
     ctx->own_stream = true;
+    if (cudaMalloc(&ctx->msm_adds_dev, 8) == cudaSuccess) cudaMemset(ctx->msm_adds_dev, 0, 8);
+    else ctx->msm_adds_dev = nullptr;
     *out = ctx;
     return B200ZK_OK;
 }
@@ -80,6 +82,7 @@ int32_t b200zk_ctx_destroy(b200zk_ctx* ctx) {
         if (s->p) cudaFree(s->p);
     for (auto& t : ctx->tables) cudaFree(t.dev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->msm_adds_dev) cudaFree(ctx->msm_adds_dev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B200ZK_OK;
@@ -426,6 +429,18 @@ int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c) {
     CHECK_CTX(ctx);
     if (c != 0 && (c < 2 || c > 24)) return fail(ctx, B200ZK_E_INVALID, "msm window %u out of range", c);
     ctx->msm_window = c;
+    return B200ZK_OK;
+}
+int32_t b200zk_msm_total_adds(b200zk_ctx* ctx, uint64_t* actual_adds, int reset) {
+    CHECK_CTX(ctx);
+    Guard g(ctx);
+    unsigned long long v = 0;
+    if (ctx->msm_adds_dev) {
+        B2_CUDA(ctx, cudaMemcpyAsync(&v, ctx->msm_adds_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (reset) B2_CUDA(ctx, cudaMemsetAsync(ctx->msm_adds_dev, 0, 8, ctx->stream));
+    }
+    if (actual_adds) *actual_adds = v;
     return B200ZK_OK;
 }
 int32_t b200zk_msm_last_stats(const b200zk_ctx* ctx, uint32_t* window_bits, uint32_t* n_windows, uint64_t* n_bucket_adds) {

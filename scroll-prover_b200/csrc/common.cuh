@@ -66,6 +66,7 @@ struct b200zk_ctx {
     uint64_t prof_cnt[b200zk::PROF_NKEYS] = {0};
     // msm knobs / stats
     uint32_t msm_window = 0;
+    unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;
     uint64_t last_adds = 0;
 };

@@ -23,10 +23,11 @@
 
 namespace b200zk {
 
-static constexpr uint32_t PART_INVALID = 0x3fffffffu;
+static constexpr uint32_t PART_INVALID = 0x1fffffffu;  // also the bucket-id mask
+static constexpr uint32_t PART_GIANT = 0x20000000u;
 static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
-static constexpr int ACC_L = 64;        // sorted entries per accumulate thread
+static constexpr int ACC_L = 128;       // sorted entries per accumulate thread
 static constexpr int GROUP = 32;        // buckets per first-level reduction group
 static constexpr uint32_t BIG_BUCKET = 4 * ACC_L;  // buckets above this size are split over threads
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_tile_sums(const uint32_t* in, u
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
-__global__ void scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total) {
+__global__ void scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total, unsigned long long* running) {
     if (threadIdx.x || blockIdx.x) return;
     uint32_t acc = 0;
     for (uint32_t i = 0; i < ntiles; ++i) {
@@ -146,6 +147,7 @@ __global__ void scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t
         acc += v;
     }
     *grand_total = acc;
+    if (running) atomicAdd(running, (unsigned long long)acc);
 }
 __global__ void __launch_bounds__(SCAN_TPB) scan_apply(const uint32_t* in, uint64_t n, const uint32_t* tile_offs, uint32_t* out,
                                                      uint32_t* out2) {
@@ -191,23 +193,12 @@ __device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
     return v;
 }
 
-__device__ __forceinline__ void accumulate_range(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries,
-                                                 uint32_t a0, uint32_t a1, XYZZ& acc) {
-    for (uint32_t pos = a0; pos < a1; ++pos) {
-        uint32_t e = entries[pos];
-        Fq px, py;
-        ld_affine(bases + (e & 0x7fffffffu), px, py);
-        if (px.is_zero() && py.is_zero()) continue;  // identity base
-        if (e & 0x80000000u) py = py.neg();
-        xyzz_madd(acc, px, py);
-    }
-}
-
-// offsets has NB + 1 entries (offsets[NB] = M sorted entries).  Thread tau has the nominal entry range
-// [tau*L, (tau+1)*L).  It OWNS every bucket of at most BIG entries that STARTS in its range (summed whole and
-// stored directly: no partials for ordinary buckets), and for buckets larger than BIG it sums only the overlap
-// with its range and emits a partial record (<= 2 per thread) that msm_combine_* merge -- so a bucket holding
-// millions of equal digits (typical witness columns) is still spread over thousands of threads.
+// offsets has NB + 1 entries (offsets[NB] = M sorted entries).  Perfect load balance: thread tau sums exactly the
+// sorted entries [tau*L, (tau+1)*L) in lock step with its warp (one mixed add per iteration for every lane).
+// Buckets that lie wholly inside the range are stored directly; the (at most two) runs cut by the range ends are
+// emitted as partial records.  Records of ordinary buckets are merged by msm_combine_heads (a bucket of <= BIG
+// entries is cut into <= BIG/L + 1 pieces); records of GIANT buckets (millions of equal digits in real witness
+// columns) go through the log-depth msm_combine_level reduction instead.
 __global__ void __launch_bounds__(256, 2)
 msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                uint64_t NB, XYZZ* __restrict__ buckets, uint32_t* __restrict__ part_id, XYZZ* __restrict__ part_val,
@@ -219,41 +210,70 @@ msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ en
     part_id[2 * tau] = PART_INVALID;
     part_id[2 * tau + 1] = PART_INVALID;
     if (start >= M) return;
-    const uint32_t lo_e = (uint32_t)start;
-    const uint32_t hi_e = (start + ACC_L < M) ? (uint32_t)(start + ACC_L) : M;
-    // largest b with offsets[b] <= lo_e  (the non-empty bucket containing entry lo_e)
-    uint64_t lo = 0, hi = NB;
+    uint32_t end = (start + ACC_L < M) ? (uint32_t)(start + ACC_L) : M;
+    uint64_t lo = 0, hi = NB;  // largest b with offsets[b] <= start
     while (hi - lo > 1) {
         uint64_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= lo_e) lo = mid; else hi = mid;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
     }
-    uint64_t b = lo;
-    uint32_t s_b = offsets[b];
+    uint32_t b = (uint32_t)lo;
+    uint32_t bucket_start = offsets[b], bucket_end = offsets[b + 1];
+    bool run_starts = (bucket_start == (uint32_t)start);
     uint32_t slot = 0;
+    XYZZ acc = XYZZ::identity();
+    uint32_t pos = (uint32_t)start;
     while (true) {
-        uint32_t e_b = offsets[b + 1];
-        uint32_t size = e_b - s_b;
-        if (size > BIG_BUCKET) {
-            uint32_t a0 = s_b > lo_e ? s_b : lo_e, a1 = e_b < hi_e ? e_b : hi_e;
-            XYZZ acc = XYZZ::identity();
-            accumulate_range(bases, entries, a0, a1, acc);
-            part_id[2 * tau + slot] = (uint32_t)b | (a0 == s_b ? PART_STARTS : 0u) | (a1 == e_b ? PART_ENDS : 0u);
-            st_xyzz(part_val + 2 * tau + slot, acc);
-            ++slot;
-        } else if (size && s_b >= lo_e) {
-            XYZZ acc = XYZZ::identity();
-            accumulate_range(bases, entries, s_b, e_b, acc);
-            st_xyzz(buckets + b, acc);
+        bool at_end = (pos == end);
+        if (at_end || pos == bucket_end) {
+            bool run_ends = (pos == bucket_end);
+            if (run_starts && run_ends) {
+                st_xyzz(buckets + b, acc);
+            } else {
+                uint32_t giant = (bucket_end - bucket_start > BIG_BUCKET) ? PART_GIANT : 0u;
+                part_id[2 * tau + slot] = b | giant | (run_starts ? PART_STARTS : 0u) | (run_ends ? PART_ENDS : 0u);
+                st_xyzz(part_val + 2 * tau + slot, acc);
+                ++slot;
+            }
+            if (at_end) break;
+            acc = XYZZ::identity();
+            bucket_start = pos;
+            do { ++b; bucket_end = offsets[b + 1]; } while (bucket_end == pos);  // skip empty buckets
+            run_starts = true;
         }
-        ++b;
-        s_b = e_b;
-        if (b >= NB || s_b >= hi_e) break;
+        uint32_t e = entries[pos];
+        Fq px, py;
+        ld_affine(bases + (e & 0x7fffffffu), px, py);
+        if (!(px.is_zero() && py.is_zero())) {
+            if (e & 0x80000000u) py = py.neg();
+            xyzz_madd(acc, px, py);
+        }
+        ++pos;
     }
 }
 
-// One level of the partial-record reduction: thread sigma scans LR consecutive records (sorted by bucket, invalid
-// slots skipped), sums runs of equal bucket id; a run that saw both the STARTS and the ENDS record is complete and
-// is stored to its bucket, otherwise it is re-emitted (<= 2 per thread) for the next level.
+// ordinary (non-giant) buckets: the head record sums the few following records up to the one that ends the bucket
+__global__ void __launch_bounds__(128) msm_combine_heads(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
+                                                         uint64_t nrec, XYZZ* __restrict__ buckets) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    uint32_t id = part_id[r];
+    if ((id & PART_INVALID) == PART_INVALID || (id & PART_GIANT) || !(id & PART_STARTS)) return;
+    XYZZ sum = ld_xyzz(part_val + r);
+    uint64_t k = r;
+    while (!(id & PART_ENDS)) {
+        ++k;
+        if (k >= nrec) break;
+        id = part_id[k];
+        if ((id & PART_INVALID) == PART_INVALID) { id = 0; continue; }
+        XYZZ v = ld_xyzz(part_val + k);
+        xyzz_add(sum, v);
+    }
+    st_xyzz(buckets + (part_id[r] & PART_INVALID), sum);
+}
+
+// One level of the GIANT-bucket reduction: thread sigma scans LR consecutive records (sorted by bucket; invalid and,
+// on the first level, non-giant records are skipped), sums runs of equal bucket id; a run that saw both the STARTS
+// and the ENDS record is complete and is stored, otherwise it is re-emitted (<= 2 per thread) for the next level.
 static constexpr int COMBINE_LR = 64;
 __global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restrict__ in_id, const XYZZ* __restrict__ in_val,
                                                          uint64_t nrec, XYZZ* __restrict__ buckets, uint32_t* __restrict__ out_id,
@@ -272,14 +292,14 @@ __global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restr
         if ((flags & PART_STARTS) && (flags & PART_ENDS)) {
             st_xyzz(buckets + cur, acc);
         } else {
-            out_id[2 * sigma + slot] = cur | flags;
+            out_id[2 * sigma + slot] = cur | flags | PART_GIANT;
             st_xyzz(out_val + 2 * sigma + slot, acc);
             ++slot;
         }
     };
     for (uint64_t r = r0; r < r1; ++r) {
         uint32_t id = in_id[r];
-        if ((id & PART_INVALID) == PART_INVALID) continue;
+        if ((id & PART_INVALID) == PART_INVALID || !(id & PART_GIANT)) continue;
         uint32_t bkt = id & PART_INVALID;
         if (!have || bkt != cur) {
             flush();
@@ -296,20 +316,20 @@ __global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restr
     flush();
 }
 
-// last level (few records): the head record of every bucket sums forward to the record that ends the bucket
+// last level (few records): the head record of every giant bucket sums forward to the record that ends it
 __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
                                                          uint64_t nrec, XYZZ* __restrict__ buckets) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
     uint32_t id = part_id[r];
-    if ((id & PART_INVALID) == PART_INVALID || !(id & PART_STARTS)) return;
+    if ((id & PART_INVALID) == PART_INVALID || !(id & PART_GIANT) || !(id & PART_STARTS)) return;
     XYZZ sum = ld_xyzz(part_val + r);
     uint64_t k = r;
     while (!(id & PART_ENDS)) {
         ++k;
         if (k >= nrec) break;
         id = part_id[k];
-        if ((id & PART_INVALID) == PART_INVALID) { id = 0; continue; }
+        if ((id & PART_INVALID) == PART_INVALID || !(id & PART_GIANT)) { id = 0; continue; }
         XYZZ v = ld_xyzz(part_val + k);
         xyzz_add(sum, v);
     }
@@ -476,7 +496,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         ProfScope ps_(ctx, PROF_MSM_SCAN);
         scan_tile_sums<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles);
         B2_LAUNCH_CHECK(ctx);
-        scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB);
+        scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB, ctx->msm_adds_dev);
         B2_LAUNCH_CHECK(ctx);
         scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles, offsets, cursor);
         B2_LAUNCH_CHECK(ctx);
@@ -498,6 +518,8 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         {
             ProfScope ps_(ctx, PROF_MSM_COMBINE);
             uint64_t nrec = 2 * nthreads;
+            msm_combine_heads<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(pid, pval, nrec, buckets);
+            B2_LAUNCH_CHECK(ctx);
             uint32_t *in_id = pid, *out_id = pid2;
             XYZZ *in_val = pval, *out_val = pval2;
             while (nrec > 2048) {

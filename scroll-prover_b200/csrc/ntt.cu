@@ -22,7 +22,7 @@
 
 namespace b200zk {
 
-static constexpr int NTT_THREADS = 512;
+static constexpr int NTT_THREADS = 256;   // 3 blocks/SM: 85 registers per thread, 72 KiB shared memory per block
 static constexpr int NTT_MAX_DIGIT = 8;
 
 struct Fr3 {
@@ -105,7 +105,7 @@ __global__ void ntt_build_table(Fr* tab, LevelRoots roots, uint32_t log_n) {
 
 // One pass over one tile.  C = lanes per tile (8, or 1 for the single-pass small transform).
 template <int C, bool LAST>
-__global__ void __launch_bounds__(NTT_THREADS, 2)
+__global__ void __launch_bounds__(NTT_THREADS, 3)
 ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict__ tab, NttPass ps, Fr3 pre_c,
                 Fr3 post_c) {
     extern __shared__ uint4 smem[];
@@ -153,9 +153,14 @@ ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __res
         rowstride = (ps.P > 1) ? (1ull << (n - ps.dig[0])) : 0;
     }
 
-    // ---- load (bit-reversed digit position), fused zero padding + coset pre-scaling on pass 0
+    // ---- load (bit-reversed digit position), fused zero padding + coset pre-scaling on pass 0.
+    // zskip: coeff_to_extended pads a 2^k vector to 2^(k+2); in pass 0 only digit entries d < L/4 are non-zero and
+    // the first two DIT stages merely replicate them 4x, so those entries are written to 4 positions and the
+    // butterfly network starts at stage 3 (saves 2 of log_n butterfly stages and 3/4 of the loads).
     const uint64_t in_len = 1ull << ps.log_in;
-    for (uint32_t e = tid; e < E; e += NT) {
+    const bool zskip = (ps.p == 0) && (ps.log_in + 2 == n) && (m >= 2);
+    const uint32_t E_load = zskip ? (E >> 2) : E, L_load = zskip ? (L >> 2) : L;
+    for (uint32_t e = tid; e < E_load; e += NT) {
         uint32_t lane, d;
         uint64_t gi;
         if (!LAST) {
@@ -163,8 +168,8 @@ ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __res
             d = e / C;
             gi = base + ((uint64_t)d << rest) + lane;
         } else {
-            d = e & (L - 1);
-            lane = e >> m;
+            d = e & (L_load - 1);
+            lane = e / L_load;
             gi = base + lane * rowstride + d;
         }
         Fr v;
@@ -178,7 +183,12 @@ ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __res
             }
         }
         uint32_t pos = __brev(d) >> (32 - m);
-        st_sm(lo, hi, idx(pos, lane), v);
+        if (zskip) {
+#pragma unroll
+            for (uint32_t r = 0; r < 4; ++r) st_sm(lo, hi, idx(pos + r, lane), v);
+        } else {
+            st_sm(lo, hi, idx(pos, lane), v);
+        }
     }
     if (!LAST) {
         for (uint32_t j = tid; j < L; j += NT) {
@@ -192,22 +202,54 @@ ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __res
     }
     __syncthreads();
 
-    // ---- m radix-2 DIT stages
-    const uint32_t nb = (L >> 1) * C;
-    for (uint32_t s = 1; s <= m; ++s) {
+    // ---- DIT stages, two per barrier (radix-4 groups held in registers), a final radix-2 stage if m is odd
+    auto twiddle = [&](uint32_t s, uint32_t K, uint32_t lane, Fr& w) -> bool {  // false when the twiddle is 1
+        if (!LAST) {
+            if (K == 0 && c == 0) return false;
+            w = ld_sm(twlo, twhi, (1u << (s - 1)) + K);
+            return true;
+        }
+        uint64_t j = ((uint64_t)K << t) + c + lane;
+        if (j == 0) return false;
+        w = ldg_fr(tab + (1ull << (t + s - 1)) + j);
+        return true;
+    };
+    uint32_t s = zskip ? 3 : 1;
+    for (; s + 1 <= m; s += 2) {
+        const uint32_t h = 1u << (s - 1);
+        const uint32_t ng = (L >> 2) * C;
+        for (uint32_t q = tid; q < ng; q += NT) {
+            uint32_t lane = q % C, gq = q / C;
+            uint32_t K = gq & (h - 1), blk = gq >> (s - 1);
+            uint32_t p = (blk << (s + 1)) + K;
+            uint32_t i0 = idx(p, lane), i1 = idx(p + h, lane), i2 = idx(p + 2 * h, lane), i3 = idx(p + 3 * h, lane);
+            Fr a = ld_sm(lo, hi, i0), b = ld_sm(lo, hi, i1), cc = ld_sm(lo, hi, i2), d = ld_sm(lo, hi, i3);
+            Fr w;
+            if (twiddle(s, K, lane, w)) {  // stage s: (a,b) and (cc,d) share w_s[K]
+                b = b * w;
+                d = d * w;
+            }
+            Fr a1 = a + b, b1 = a - b, c1 = cc + d, d1 = cc - d;
+            if (twiddle(s + 1, K, lane, w)) c1 = c1 * w;  // stage s+1: (a1,c1) with w_{s+1}[K]
+            twiddle(s + 1, K + h, lane, w);               //            (b1,d1) with w_{s+1}[K+h]  (never 1)
+            d1 = d1 * w;
+            st_sm(lo, hi, i0, a1 + c1);
+            st_sm(lo, hi, i2, a1 - c1);
+            st_sm(lo, hi, i1, b1 + d1);
+            st_sm(lo, hi, i3, b1 - d1);
+        }
+        __syncthreads();
+    }
+    if (s == m) {
         const uint32_t half = 1u << (s - 1);
+        const uint32_t nb = (L >> 1) * C;
         for (uint32_t b = tid; b < nb; b += NT) {
             uint32_t lane = b % C, bb = b / C;
             uint32_t K = bb & (half - 1), blk = bb >> (s - 1);
             uint32_t p0 = (blk << s) + K, p1 = p0 + half;
             uint32_t i0 = idx(p0, lane), i1 = idx(p1, lane);
-            Fr u = ld_sm(lo, hi, i0), v = ld_sm(lo, hi, i1);
-            if (!LAST) {
-                if (K != 0 || c != 0) v = v * ld_sm(twlo, twhi, half + K);
-            } else {
-                uint64_t j = ((uint64_t)K << t) + c + lane;
-                if (j != 0) v = v * ldg_fr(tab + (1ull << (t + s - 1)) + j);
-            }
+            Fr u = ld_sm(lo, hi, i0), v = ld_sm(lo, hi, i1), w;
+            if (twiddle(s, K, lane, w)) v = v * w;
             st_sm(lo, hi, i0, u + v);
             st_sm(lo, hi, i1, u - v);
         }
@@ -331,7 +373,7 @@ static int32_t launch_pass(b200zk_ctx* ctx, const Fr* in, Fr* out, const Fr* tab
         attr_set = true;
     }
     uint64_t tiles = (1ull << ps.log_n) / E;
-    uint32_t nb = (L >> 1) * C;
+    uint32_t nb = (L >> 2) * C;  // radix-4 groups per double stage
     uint32_t threads = nb >= NTT_THREADS ? NTT_THREADS : (nb < 32 ? 32 : nb);
     {
         ProfScope psc(ctx, PROF_NTT_PASS);
