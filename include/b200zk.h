@@ -77,6 +77,10 @@ B200ZK_API int32_t b200zk_buf_download(b200zk_ctx* ctx, void* host, const void* 
  * reference call sites /root/reference/bin/src/trace_prover.rs:35-36, integration/src/prove.rs:12):
  * uploads n affine bases once; they stay resident for the life of the handle. */
 B200ZK_API int32_t b200zk_srs_register(b200zk_ctx* ctx, const void* g1_affine, uint64_t n, uint32_t tag, b200zk_srs** out);
+/* mode 1 (default): handles of >= 2^16 points also keep the multiples 2^(c*w) P_i of every base (W x the
+ * storage, built once at registration) when device memory allows, so all Pippenger windows share one bucket
+ * set; mode 0: plain bases only.  Applies to subsequent b200zk_srs_register calls. */
+B200ZK_API int32_t b200zk_srs_set_precompute(b200zk_ctx* ctx, int mode);
 B200ZK_API int32_t b200zk_srs_release(b200zk_ctx* ctx, b200zk_srs* srs);
 B200ZK_API int32_t b200zk_srs_len(const b200zk_srs* srs, uint64_t* out);
 

@@ -69,6 +69,7 @@ def _load():
         "b200zk_buf_download": [vp, vp, vp, u64],
         "b200zk_srs_register": [vp, vp, u64, u32, C.POINTER(vp)],
         "b200zk_srs_release": [vp, vp],
+        "b200zk_srs_set_precompute": [vp, C.c_int],
         "b200zk_srs_len": [vp, C.POINTER(u64)],
         "b200zk_msm_g1": [vp, vp, vp, u64, vp],
         "b200zk_msm_g1_bases": [vp, vp, vp, u64, vp],
@@ -104,7 +105,7 @@ def _load():
 ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
-    "b200zk_srs_register", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
+    "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
@@ -203,6 +204,9 @@ class Context:
     # ---- SRS / MSM
     def srs_register(self, bases, tag: int = SRS_G) -> "Srs":
         return Srs(self, bases, tag)
+
+    def srs_set_precompute(self, on: bool):
+        self._ck(lib().b200zk_srs_set_precompute(self._h, int(on)))
 
     def msm_set_window(self, c: int):
         self._ck(lib().b200zk_msm_set_window(self._h, c))

@@ -6,7 +6,10 @@
 #include "ec.cuh"
 
 namespace b200zk {
-int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev);
+int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev, uint32_t pre_c,
+                uint64_t pre_stride);
+uint32_t msm_pick_window_precomputed(uint64_t n);
+int32_t srs_precompute_run(b200zk_ctx* ctx, Affine* tables, uint64_t n, uint32_t c, uint32_t W);
 int32_t g1_sum_run(b200zk_ctx* ctx, const Jacobian* pts, uint64_t count, Jacobian* out_dev);
 int32_t g1_generator_mul_run(b200zk_ctx* ctx, const Fr* scalars, uint64_t n, Affine* out);
 int32_t poly_ew(b200zk_ctx* ctx, int op, Fr* r, const Fr* a, const Fr* b, const Fr& s, uint64_t n);
@@ -168,7 +171,20 @@ int32_t b200zk_srs_register(b200zk_ctx* ctx, const void* g1_affine, uint64_t n, 
     s->n = n;
     s->tag = tag;
     s->dev_bases = nullptr;
+    s->pre_c = 0;
+    s->pre_W = 1;
     size_t bytes = sizeof(Affine) * (n ? n : 1);
+    if (ctx->srs_precompute && n >= (1ull << 16)) {
+        // keep 2^(c*w) * P_i for every window w: all windows then share ONE bucket set (no per-window reduction, no
+        // Horner doublings) and a wider window pays off.  Costs W x the base storage; skipped when memory is short.
+        uint32_t c = msm_pick_window_precomputed(n), W = 254 / c + 1;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)bytes * W < 0.35 * (double)free_b) {
+            s->pre_c = c;
+            s->pre_W = W;
+            bytes *= W;
+        }
+    }
     cudaError_t e = cudaMalloc(&s->dev_bases, bytes);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
@@ -182,6 +198,15 @@ int32_t b200zk_srs_register(b200zk_ctx* ctx, const void* g1_affine, uint64_t n, 
         cudaFree(s->dev_bases);
         delete s;
         return fail(ctx, B200ZK_E_CUDA, "srs_register: upload failed: %s", cudaGetErrorString(e));
+    }
+    if (s->pre_c) {
+        int32_t rc = srs_precompute_run(ctx, (Affine*)s->dev_bases, n, s->pre_c, s->pre_W);
+        if (rc == B200ZK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200ZK_E_CUDA;
+        if (rc != B200ZK_OK) {
+            cudaFree(s->dev_bases);
+            delete s;
+            return fail(ctx, rc, "srs_register: precomputation failed");
+        }
     }
     *out = s;
     return B200ZK_OK;
@@ -202,12 +227,13 @@ int32_t b200zk_srs_len(const b200zk_srs* srs, uint64_t* out) {
 }
 
 // ---- MSM ---------------------------------------------------------------------------------------
-static int32_t msm_common(b200zk_ctx* ctx, const Affine* bases_dev, const void* scalars, uint64_t n, void* out96) {
+static int32_t msm_common(b200zk_ctx* ctx, const Affine* bases_dev, const void* scalars, uint64_t n, void* out96,
+                          uint32_t pre_c = 0, uint64_t pre_stride = 0) {
     const void* sc_dev = nullptr;
     if (n) B2_TRY(stage_in(ctx, ctx->stage_in, scalars, sizeof(Fr) * n, &sc_dev));
     B2_TRY(scratch_reserve(ctx, ctx->stage_out, 256));
     Jacobian* res = (Jacobian*)ctx->stage_out.p;
-    B2_TRY(msm_run(ctx, bases_dev, (const Fr*)sc_dev, n, res));
+    B2_TRY(msm_run(ctx, bases_dev, (const Fr*)sc_dev, n, res, pre_c, pre_stride));
     return deliver(ctx, out96, res, sizeof(Jacobian));
 }
 
@@ -219,7 +245,7 @@ int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalar
         return fail(ctx, B200ZK_E_INVALID, "msm_g1: %llu scalars but only %llu bases (assert_eq!(coeffs.len(), bases.len()))",
                     (unsigned long long)n, (unsigned long long)srs->n);
     Guard g(ctx);
-    return msm_common(ctx, (const Affine*)srs->dev_bases, scalars, n, out_jacobian96);
+    return msm_common(ctx, (const Affine*)srs->dev_bases, scalars, n, out_jacobian96, srs->pre_c, srs->n);
 }
 
 int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96) {
@@ -425,6 +451,12 @@ int32_t b200zk_profile_read(b200zk_ctx* ctx, const char* name, double* total_ms,
     return fail(ctx, B200ZK_E_INVALID, "profile_read: unknown kernel class '%s'", name);
 }
 
+int32_t b200zk_srs_set_precompute(b200zk_ctx* ctx, int mode) {
+    CHECK_CTX(ctx);
+    if (mode != 0 && mode != 1) return fail(ctx, B200ZK_E_INVALID, "srs_set_precompute: mode must be 0 or 1");
+    ctx->srs_precompute = mode;
+    return B200ZK_OK;
+}
 int32_t b200zk_msm_set_window(b200zk_ctx* ctx, uint32_t c) {
     CHECK_CTX(ctx);
     if (c != 0 && (c < 2 || c > 24)) return fail(ctx, B200ZK_E_INVALID, "msm window %u out of range", c);

@@ -40,9 +40,11 @@ struct Scratch {  // grow-only device allocation
 
 struct b200zk_srs {
     b200zk_ctx* ctx;
-    void* dev_bases;  // n x 64 B affine (x,y Montgomery Fq)
+    void* dev_bases;  // n x 64 B affine (x,y Montgomery Fq); W tables back to back when precomputed
     uint64_t n;
     uint32_t tag;
+    uint32_t pre_c;   // 0: plain bases; else window bits the 2^(c*w) tables were built for
+    uint32_t pre_W;
 };
 
 struct b200zk_ctx {
@@ -66,6 +68,7 @@ struct b200zk_ctx {
     uint64_t prof_cnt[b200zk::PROF_NKEYS] = {0};
     // msm knobs / stats
     uint32_t msm_window = 0;
+    int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;
     uint64_t last_adds = 0;

@@ -33,8 +33,10 @@ static constexpr uint32_t BIG_BUCKET = 4 * ACC_L;  // buckets above this size ar
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
-    uint64_t NB;        // W * B
-    uint32_t g, G;      // reduction group size, groups per window
+    uint32_t Ws;        // bucket sets: W, or 1 when the SRS holds precomputed 2^(c*w) multiples of every base
+    uint64_t stride;    // precomputed SRS: table w starts at bases + w*stride (0 otherwise)
+    uint64_t NB;        // Ws * B
+    uint32_t g, G;      // reduction group size, groups per bucket set
 };
 
 __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, 
                 carry = 0;
             }
             digits[(uint64_t)w * n + i] = enc;
-            if (enc) atomicAdd(&hist[(uint64_t)w * pl.B + (enc & 0x7fffffffu) - 1], 1u);
+            if (enc) atomicAdd(&hist[(pl.Ws == 1 ? 0ull : (uint64_t)w * pl.B) + (enc & 0x7fffffffu) - 1], 1u);
         }
     }
 }
@@ -92,8 +94,8 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
         if (!d) continue;
         uint64_t w = idx / n;
         uint32_t i = (uint32_t)(idx - w * n);
-        uint32_t pos = atomicAdd(&cursor[w * pl.B + (d & 0x7fffffffu) - 1], 1u);
-        entries[pos] = i | (d & 0x80000000u);
+        uint32_t pos = atomicAdd(&cursor[(pl.Ws == 1 ? 0ull : w * pl.B) + (d & 0x7fffffffu) - 1], 1u);
+        entries[pos] = (uint32_t)(i + w * pl.stride) | (d & 0x80000000u);
     }
 }
 
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restr
 __global__ void __launch_bounds__(128) msm_group_reduce(const XYZZ* __restrict__ buckets, MsmPlan pl, XYZZ* __restrict__ grpR,
                                                         XYZZ* __restrict__ grpW) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t total = (uint64_t)pl.W * pl.G;
+    uint64_t total = (uint64_t)pl.Ws * pl.G;
     if (t >= total) return;
     uint32_t w = (uint32_t)(t / pl.G), j = (uint32_t)(t % pl.G);
     const XYZZ* bk = buckets + (uint64_t)w * pl.B + (uint64_t)j * pl.g;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(128) msm_tree_level(MsmPlan pl, uint32_t level
                                                       XYZZ* __restrict__ grpW) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t pairs = pl.G >> (level + 1);
-    uint64_t total = (uint64_t)pl.W * pairs;
+    uint64_t total = (uint64_t)pl.Ws * pairs;
     if (t >= total) return;
     uint32_t w = (uint32_t)(t / pairs), k = (uint32_t)(t % pairs);
     uint64_t i = (uint64_t)w * pl.G + ((uint64_t)k << (level + 1)), i2 = i + (1ull << level);
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(128) msm_tree_level(MsmPlan pl, uint32_t level
 __global__ void msm_finish(MsmPlan pl, const XYZZ* __restrict__ grpW, Jacobian* out) {
     if (threadIdx.x || blockIdx.x) return;
     XYZZ acc = XYZZ::identity();
-    for (uint32_t w = pl.W; w-- > 0;) {
+    for (uint32_t w = pl.Ws; w-- > 0;) {
         for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);
         XYZZ s = ld_xyzz(grpW + (uint64_t)w * pl.G);
         xyzz_add(acc, s);
@@ -430,14 +432,52 @@ static uint32_t pick_window(uint64_t n) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev) {
+// out[i] = 2^c * in[i] (affine): one table of the precomputed SRS from the previous one
+__global__ void __launch_bounds__(128) srs_shift_kernel(const Affine* __restrict__ in, Affine* __restrict__ out, uint64_t n, uint32_t c) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine a = in[i];
+    XYZZ p = xyzz_from_affine(a);
+    for (uint32_t d = 0; d < c; ++d) p = xyzz_dbl(p);
+    out[i] = xyzz_to_affine(p);
+}
+
+uint32_t msm_pick_window_precomputed(uint64_t n) {
+    double best = 1e300;
+    uint32_t bc = 10;
+    for (uint32_t c = 8; c <= 23; ++c) {
+        uint32_t W = 254 / c + 1;
+        if ((double)n * W >= 2.0e9) continue;  // entry = table index (31 bits) | sign
+        double cost = (double)n * W * 10.0 + (double)(1ull << c) * 16.0;
+        if (cost < best) {
+            best = cost;
+            bc = c;
+        }
+    }
+    return bc;
+}
+
+// tables[w] = 2^(c*w) * bases, w = 0..W-1, laid out back to back (stride n); tables[0] must already hold the bases
+int32_t srs_precompute_run(b200zk_ctx* ctx, Affine* tables, uint64_t n, uint32_t c, uint32_t W) {
+    for (uint32_t w = 1; w < W; ++w) {
+        srs_shift_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(tables + (uint64_t)(w - 1) * n, tables + (uint64_t)w * n, n, c);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    return B200ZK_OK;
+}
+
+// pre_c != 0: `bases` is a precomputed SRS (W tables of stride pre_stride) built for window pre_c
+int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev, uint32_t pre_c,
+                uint64_t pre_stride) {
     if (n >= (1ull << 31)) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n = %llu >= 2^31", (unsigned long long)n);
     MsmPlan pl;
-    pl.c = ctx->msm_window ? ctx->msm_window : pick_window(n);
+    pl.c = pre_c ? pre_c : (ctx->msm_window ? ctx->msm_window : pick_window(n));
     if (pl.c < 2 || pl.c > 24) return fail(ctx, B200ZK_E_INVALID, "msm: window %u out of range [2,24]", pl.c);
     pl.W = 254 / pl.c + 1;
     pl.B = 1u << (pl.c - 1);
-    pl.NB = (uint64_t)pl.W * pl.B;
+    pl.Ws = pre_c ? 1 : pl.W;
+    pl.stride = pre_c ? pre_stride : 0;
+    pl.NB = (uint64_t)pl.Ws * pl.B;
     pl.g = pl.B < (uint32_t)GROUP ? pl.B : (uint32_t)GROUP;
     pl.G = pl.B / pl.g;
     uint32_t log_g = 0;
@@ -462,7 +502,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     size_t o_pid = carve(4 * 2 * nthreads), o_pval = carve(sizeof(XYZZ) * 2 * nthreads);
     uint64_t nthreads2 = (2 * nthreads + COMBINE_LR - 1) / COMBINE_LR;
     size_t o_pid2 = carve(4 * 2 * nthreads2), o_pval2 = carve(sizeof(XYZZ) * 2 * nthreads2);
-    size_t o_gr = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G), o_gw = carve(sizeof(XYZZ) * (size_t)pl.W * pl.G);
+    size_t o_gr = carve(sizeof(XYZZ) * (size_t)pl.Ws * pl.G), o_gw = carve(sizeof(XYZZ) * (size_t)pl.Ws * pl.G);
     B2_TRY(scratch_reserve(ctx, ctx->msm_work, off));
     char* base = (char*)ctx->msm_work.p;
     uint32_t* hist = (uint32_t*)(base + o_hist);
@@ -536,11 +576,11 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     }
     {
         ProfScope ps_(ctx, PROF_MSM_REDUCE);
-        uint64_t total = (uint64_t)pl.W * pl.G;
+        uint64_t total = (uint64_t)pl.Ws * pl.G;
         msm_group_reduce<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(buckets, pl, grpR, grpW);
         B2_LAUNCH_CHECK(ctx);
         for (uint32_t level = 0; (pl.G >> level) > 1; ++level) {
-            uint64_t t2 = (uint64_t)pl.W * (pl.G >> (level + 1));
+            uint64_t t2 = (uint64_t)pl.Ws * (pl.G >> (level + 1));
             msm_tree_level<<<(uint32_t)((t2 + 127) / 128), 128, 0, st>>>(pl, level, log_g, grpR, grpW);
             B2_LAUNCH_CHECK(ctx);
         }

@@ -244,6 +244,27 @@ def test_params_kzg_commit_and_commit_lagrange(ctx, zk):
     params.release()
 
 
+def test_precomputed_srs_matches_plain_and_oracle(ctx):
+    """SRS handles of >= 2^16 points keep 2^(c*w) multiples (single bucket set); results must not change."""
+    n = 1 << 16
+    bases = O.fill_points_chain(n, 77, 16)
+    scal = O.fill_fr(n, SEED + 800)
+    wl = O.fill_fr(n, SEED + 801, witness_like=True)
+    exp_u = norm_affine(O.best_multiexp(scal, bases, threads=16))
+    exp_w = norm_affine(O.best_multiexp(wl, bases, threads=16))
+    exp_short = norm_affine(O.best_multiexp(scal[:1000], bases[:1000], threads=4))
+    for mode in (True, False):
+        ctx.srs_set_precompute(mode)
+        try:
+            srs = ctx.srs_register(bases)
+        finally:
+            ctx.srs_set_precompute(True)
+        assert np.array_equal(norm_affine(srs.msm(scal)), exp_u), mode
+        assert np.array_equal(norm_affine(srs.msm(wl)), exp_w), mode
+        assert np.array_equal(norm_affine(srs.msm(scal[:1000])), exp_short), mode  # commit over the first len bases
+        srs.release()
+
+
 def test_large_msm_properties(ctx, zk):
     """BASELINE config 1 size (2^20): device-generated SRS g[i] = tau^i G, commit(p) == p(tau) G,
     linearity, and agreement with the multi-threaded oracle on the same inputs."""
