@@ -339,50 +339,101 @@ __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restr
 }
 
 // ---- bucket reduction ---------------------------------------------------------------------------
-// group j of window w covers bucket values j*g+1 .. j*g+g:  R = sum B_b,  Wt = sum (b - j*g) B_b
-__global__ void __launch_bounds__(128) msm_group_reduce(const XYZZ* __restrict__ buckets, MsmPlan pl, XYZZ* __restrict__ grpR,
-                                                        XYZZ* __restrict__ grpW) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t total = (uint64_t)pl.Ws * pl.G;
-    if (t >= total) return;
-    uint32_t w = (uint32_t)(t / pl.G), j = (uint32_t)(t % pl.G);
-    const XYZZ* bk = buckets + (uint64_t)w * pl.B + (uint64_t)j * pl.g;
-    XYZZ run = XYZZ::identity(), ws = XYZZ::identity();
-    for (uint32_t i = pl.g; i-- > 0;) {
-        XYZZ v = ld_xyzz(bk + i);
-        xyzz_add(run, v);
-        xyzz_add(ws, run);
+// S = sum_{i<B} (i+1) B_i for every bucket set, with a SHORT critical path (the old running-sum + doubling tree had
+// ~100 dependent point additions and ~200 dependent doublings; this has ~40 additions and kc doublings):
+// view the set as a matrix i = hi*2^kc + lo;  Row_hi = sum_lo B, Col_lo = sum_hi B   (block tree sums), then
+//   S = WS(Col) + 2^kc * WS(Row) + sum(Row),     WS(V) = sum_j j V_j = sum_{j>=1} Suffix_j(V)   (parallel suffix scan).
+static constexpr int RED_T = 256;
+
+__device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {  // result valid in thread 0
+    st_xyzz(sh + threadIdx.x, v);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            XYZZ a = ld_xyzz(sh + threadIdx.x), b = ld_xyzz(sh + threadIdx.x + s);
+            xyzz_add(a, b);
+            st_xyzz(sh + threadIdx.x, a);
+        }
+        __syncthreads();
     }
-    st_xyzz(grpR + t, run);
-    st_xyzz(grpW + t, ws);
+    v = ld_xyzz(sh);
 }
 
-// level l: segment i (multiple of 2^(l+1)) absorbs segment i + 2^l:  R += R',  Wt += Wt' + (2^l * g) R'
-__global__ void __launch_bounds__(128) msm_tree_level(MsmPlan pl, uint32_t level, uint32_t log_g, XYZZ* __restrict__ grpR,
-                                                      XYZZ* __restrict__ grpW) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t pairs = pl.G >> (level + 1);
-    uint64_t total = (uint64_t)pl.Ws * pairs;
-    if (t >= total) return;
-    uint32_t w = (uint32_t)(t / pairs), k = (uint32_t)(t % pairs);
-    uint64_t i = (uint64_t)w * pl.G + ((uint64_t)k << (level + 1)), i2 = i + (1ull << level);
-    XYZZ r1 = ld_xyzz(grpR + i), r2 = ld_xyzz(grpR + i2);
-    XYZZ w1 = ld_xyzz(grpW + i), w2 = ld_xyzz(grpW + i2);
-    xyzz_add(w1, w2);
-    XYZZ sh = r2;
-    for (uint32_t d = 0; d < level + log_g; ++d) sh = xyzz_dbl(sh);
-    xyzz_add(w1, sh);
-    xyzz_add(r1, r2);
-    st_xyzz(grpR + i, r1);
-    st_xyzz(grpW + i, w1);
+// grid = (rows + cols, Ws); block j < rows sums row j, block rows + j sums column j.  vec[set][0..rows) | [rows..rows+cols)
+__global__ void __launch_bounds__(RED_T) msm_rowcol_sums(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t kc, XYZZ* __restrict__ vec) {
+    __shared__ XYZZ sh[RED_T];
+    const uint32_t cols = 1u << kc, rows = B >> kc;
+    const XYZZ* bk = buckets + (uint64_t)blockIdx.y * B;
+    XYZZ acc = XYZZ::identity();
+    if (blockIdx.x < rows) {
+        const XYZZ* r = bk + (uint64_t)blockIdx.x * cols;
+        for (uint32_t lo = threadIdx.x; lo < cols; lo += blockDim.x) {
+            XYZZ v = ld_xyzz(r + lo);
+            xyzz_add(acc, v);
+        }
+    } else {
+        uint32_t lo = blockIdx.x - rows;
+        for (uint32_t hi = threadIdx.x; hi < rows; hi += blockDim.x) {
+            XYZZ v = ld_xyzz(bk + (uint64_t)hi * cols + lo);
+            xyzz_add(acc, v);
+        }
+    }
+    block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) st_xyzz(vec + (uint64_t)blockIdx.y * (rows + cols) + blockIdx.x, acc);
 }
 
-__global__ void msm_finish(MsmPlan pl, const XYZZ* __restrict__ grpW, Jacobian* out) {
+// grid = (2, Ws), 512 threads: block 0 handles the Row vector, block 1 the Col vector of its set.
+// out[set][0] = WS(Row), out[set][1] = sum(Row), out[set][2] = WS(Col).  tmp: 2 x (rows+cols) per set (ping-pong).
+__global__ void __launch_bounds__(512) msm_weighted_sums(XYZZ* __restrict__ vec, XYZZ* __restrict__ tmp, uint32_t B, uint32_t kc,
+                                                          XYZZ* __restrict__ out) {
+    const uint32_t cols = 1u << kc, rows = B >> kc;
+    const uint32_t m = blockIdx.x == 0 ? rows : cols;
+    const uint64_t setoff = (uint64_t)blockIdx.y * (rows + cols) + (blockIdx.x == 0 ? 0 : rows);
+    XYZZ* cur = vec + setoff;
+    XYZZ* nxt = tmp + setoff;
+    // inclusive suffix scan (Hillis-Steele): cur[j] = sum_{i>=j} V_i
+    for (uint32_t d = 1; d < m; d <<= 1) {
+        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+            XYZZ a = ld_xyzz(cur + j);
+            if (j + d < m) {
+                XYZZ b2 = ld_xyzz(cur + j + d);
+                xyzz_add(a, b2);
+            }
+            st_xyzz(nxt + j, a);
+        }
+        __syncthreads();
+        XYZZ* t = cur; cur = nxt; nxt = t;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) st_xyzz(out + (uint64_t)blockIdx.y * 3 + 1, ld_xyzz(cur));  // sum(Row) = Suffix_0
+    __syncthreads();
+    // WS = sum_{j>=1} Suffix_j : pairwise tree over the live elements cur[1 .. live]
+    uint32_t live = m - 1;
+    while (live > 1) {
+        uint32_t half = (live + 1) >> 1;
+        for (uint32_t q = threadIdx.x; q + half < live; q += blockDim.x) {
+            XYZZ a = ld_xyzz(cur + 1 + q), b2 = ld_xyzz(cur + 1 + q + half);
+            xyzz_add(a, b2);
+            st_xyzz(cur + 1 + q, a);
+        }
+        __syncthreads();
+        live = half;
+    }
+    if (threadIdx.x == 0) {
+        XYZZ r = (m >= 2) ? ld_xyzz(cur + 1) : XYZZ::identity();
+        st_xyzz(out + (uint64_t)blockIdx.y * 3 + (blockIdx.x == 0 ? 0 : 2), r);
+    }
+}
+
+__global__ void msm_finish(MsmPlan pl, uint32_t kc, const XYZZ* __restrict__ sums, Jacobian* out) {
     if (threadIdx.x || blockIdx.x) return;
     XYZZ acc = XYZZ::identity();
     for (uint32_t w = pl.Ws; w-- > 0;) {
-        for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);
-        XYZZ s = ld_xyzz(grpW + (uint64_t)w * pl.G);
+        for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);   // no-op while acc is the identity (Ws == 1)
+        XYZZ s = ld_xyzz(sums + (uint64_t)w * 3);                  // WS(Row)
+        for (uint32_t d = 0; d < kc; ++d) s = xyzz_dbl(s);
+        XYZZ t = ld_xyzz(sums + (uint64_t)w * 3 + 1), u = ld_xyzz(sums + (uint64_t)w * 3 + 2);
+        xyzz_add(s, t);
+        xyzz_add(s, u);
         xyzz_add(acc, s);
     }
     *out = xyzz_to_jacobian_normalized(acc);
@@ -480,8 +531,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     pl.NB = (uint64_t)pl.Ws * pl.B;
     pl.g = pl.B < (uint32_t)GROUP ? pl.B : (uint32_t)GROUP;
     pl.G = pl.B / pl.g;
-    uint32_t log_g = 0;
-    while ((1u << log_g) < pl.g) ++log_g;
     uint64_t max_entries = n * pl.W;
     if (max_entries >= 0xffffffffull) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n*W too large for window %u", pl.c);
     ctx->last_c = pl.c;
@@ -502,7 +551,10 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     size_t o_pid = carve(4 * 2 * nthreads), o_pval = carve(sizeof(XYZZ) * 2 * nthreads);
     uint64_t nthreads2 = (2 * nthreads + COMBINE_LR - 1) / COMBINE_LR;
     size_t o_pid2 = carve(4 * 2 * nthreads2), o_pval2 = carve(sizeof(XYZZ) * 2 * nthreads2);
-    size_t o_gr = carve(sizeof(XYZZ) * (size_t)pl.Ws * pl.G), o_gw = carve(sizeof(XYZZ) * (size_t)pl.Ws * pl.G);
+    const uint32_t kc = pl.c / 2;                       // columns = 2^kc, rows = B / 2^kc  (c - 1 = kc + kr)
+    const uint32_t red_cols = 1u << kc, red_rows = pl.B >> kc;
+    size_t red_len = (size_t)pl.Ws * (red_rows + red_cols);
+    size_t o_gr = carve(sizeof(XYZZ) * red_len), o_gw = carve(sizeof(XYZZ) * red_len), o_sums = carve(sizeof(XYZZ) * 3 * pl.Ws);
     B2_TRY(scratch_reserve(ctx, ctx->msm_work, off));
     char* base = (char*)ctx->msm_work.p;
     uint32_t* hist = (uint32_t*)(base + o_hist);
@@ -518,6 +570,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     XYZZ* pval = (XYZZ*)(base + o_pval);
     XYZZ* grpR = (XYZZ*)(base + o_gr);
     XYZZ* grpW = (XYZZ*)(base + o_gw);
+    XYZZ* red_sums = (XYZZ*)(base + o_sums);
 
     cudaStream_t st = ctx->stream;
     B2_CUDA(ctx, cudaMemsetAsync(hist, 0, 4 * (pl.NB + 1), st));
@@ -576,15 +629,11 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     }
     {
         ProfScope ps_(ctx, PROF_MSM_REDUCE);
-        uint64_t total = (uint64_t)pl.Ws * pl.G;
-        msm_group_reduce<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(buckets, pl, grpR, grpW);
+        msm_rowcol_sums<<<dim3(red_rows + red_cols, pl.Ws), RED_T, 0, st>>>(buckets, pl.B, kc, grpR);
         B2_LAUNCH_CHECK(ctx);
-        for (uint32_t level = 0; (pl.G >> level) > 1; ++level) {
-            uint64_t t2 = (uint64_t)pl.Ws * (pl.G >> (level + 1));
-            msm_tree_level<<<(uint32_t)((t2 + 127) / 128), 128, 0, st>>>(pl, level, log_g, grpR, grpW);
-            B2_LAUNCH_CHECK(ctx);
-        }
-        msm_finish<<<1, 32, 0, st>>>(pl, grpW, out_dev);
+        msm_weighted_sums<<<dim3(2, pl.Ws), 512, 0, st>>>(grpR, grpW, pl.B, kc, red_sums);
+        B2_LAUNCH_CHECK(ctx);
+        msm_finish<<<1, 32, 0, st>>>(pl, kc, red_sums, out_dev);
         B2_LAUNCH_CHECK(ctx);
     }
     return B200ZK_OK;
