@@ -51,6 +51,45 @@ __global__ void k_imad_wide(uint64_t* out, uint32_t a, uint32_t b, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 pipe: independent DFMA chains (B200 keeps full-rate FP64, unlike B300) -- experiment for a 52-bit-limb
+// floating-point modular multiplier running beside the INT32 pipe
+template <int ILP>
+__global__ void k_dfma(double* out, double a, double b, int iters) {
+    double acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x + i;
+    for (int k = 0; k < iters; ++k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// both pipes at once: one IMAD.WIDE-bound Montgomery product chain + independent DFMA chains in the same thread
+template <int NDF>
+__global__ void k_mix(Fr* data, double* out, double a, double b, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fr y = data[t], x = y;
+    x.l.v[7] &= 0x0fffffff;
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x + i;
+    for (int k = 0; k < iters; ++k) {
+        x = x * y;
+#pragma unroll
+        for (int u = 0; u < NDF; ++u) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[u & 7]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    data[t] = x;
+    out[t] = s;
+}
+
 template <class F, int ILP>
 __global__ void k_fmul(F* data, int iters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,6 +164,22 @@ int main() {
             ms = time_ms([&] { k_imad_wide<8><<<blocks, tpb>>>((uint64_t*)buf, 3, 5, iters); });
             printf("{\"bench\": \"imad_wide\", \"tpb\": %d, \"blocks_per_sm\": %d, \"ms\": %.3f, \"Gmac32\": %.1f}\n", tpb, bps, ms, ops / ms / 1e6);
         }
+    }
+    for (int bps : {2, 4, 8}) {
+        int blocks = sms * bps, tpb = 256;
+        double ms = time_ms([&] { k_dfma<8><<<blocks, tpb>>>((double*)buf, 1.0000001, 0.5, iters); });
+        double ops = (double)blocks * tpb * iters * 8 * 8;
+        printf("{\"bench\": \"dfma\", \"tpb\": %d, \"blocks_per_sm\": %d, \"ms\": %.3f, \"Gdfma\": %.1f}\n", tpb, bps, ms, ops / ms / 1e6);
+    }
+    {
+        int blocks = sms * 4, tpb = 256, it = 500;
+        double* dout = (double*)((char*)buf + (32ull << 20));
+        double ms0 = time_ms([&] { k_mix<0><<<blocks, tpb>>>((Fr*)buf, dout, 1.0000001, 0.5, it); });
+        double ms64 = time_ms([&] { k_mix<64><<<blocks, tpb>>>((Fr*)buf, dout, 1.0000001, 0.5, it); });
+        double ms128 = time_ms([&] { k_mix<128><<<blocks, tpb>>>((Fr*)buf, dout, 1.0000001, 0.5, it); });
+        double muls = (double)blocks * tpb * it;
+        printf("{\"bench\": \"mix_frmul_plus_dfma\", \"ms_mul_only\": %.3f, \"ms_plus64dfma\": %.3f, \"ms_plus128dfma\": %.3f, \"Gmul_only\": %.2f, \"Gmul_with128\": %.2f, \"Gdfma_with128\": %.1f}\n",
+               ms0, ms64, ms128, muls / ms0 / 1e6, muls / ms128 / 1e6, muls * 128 / ms128 / 1e6);
     }
     const int miters = 500;
 #define RUN_F(NAME, KERN, ILP, TPB, BPS)                                                                       \

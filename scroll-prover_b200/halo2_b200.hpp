@@ -1,0 +1,279 @@
+// halo2_b200.hpp — C++ host-side mirror of the halo2_proofs functions that libb200zk replaces.
+//
+// The reference's host language is Rust (no toolchain in this image), so the host layer above the C ABI
+// (include/b200zk.h) is provided in C++ with the SAME names, argument meaning and failure behaviour as
+// halo2_proofs 1.1.0 (scroll-tech/halo2 @ e5ddf67, pin /root/reference/Cargo.lock:1886-1888):
+//
+//   halo2_b200::arithmetic::best_multiexp / best_fft / eval_polynomial / kate_division   (src/arithmetic.rs)
+//   halo2_b200::EvaluationDomain::{new_, lagrange_to_coeff, coeff_to_extended, extended_to_coeff}  (src/poly/domain.rs)
+//   halo2_b200::ParamsKZG::{setup, read_custom, write_custom, commit, commit_lagrange, downsize-less accessors}
+//                                                                                    (src/poly/kzg/commitment.rs)
+// A Rust panic (assert_eq!, unwrap) is mirrored by throwing halo2_b200::Panic.  Types are layout-identical to
+// halo2curves::bn256::{Fr, G1Affine, G1} (raw Montgomery limbs).  Header-only; link with -lb200zk.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/b200zk.h"
+#include "csrc/ff.cuh"  // host emulation of the field layer for the (tiny) domain-constant computations
+
+namespace halo2_b200 {
+
+struct Panic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct Fr {
+    uint64_t l[4];
+    bool operator==(const Fr& o) const { return std::memcmp(l, o.l, 32) == 0; }
+};
+struct Fq {
+    uint64_t l[4];
+};
+struct G1Affine {
+    Fq x, y;  // identity = (0, 0)
+};
+struct G1 {
+    Fq x, y, z;  // Jacobian, identity z = 0
+    bool is_identity() const { return (z.l[0] | z.l[1] | z.l[2] | z.l[3]) == 0; }
+};
+static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 64 && sizeof(G1) == 96, "ABI layout");
+
+namespace detail {
+using DFr = b200zk::Fr;
+inline DFr to_dev(const Fr& a) {
+    DFr r;
+    std::memcpy(r.l.v, a.l, 32);
+    return r;
+}
+inline Fr from_dev(const DFr& a) {
+    Fr r;
+    std::memcpy(r.l, a.l.v, 32);
+    return r;
+}
+inline DFr from_u64(uint64_t v) {
+    DFr t = DFr::zero();
+    t.l.v[0] = (uint32_t)v;
+    t.l.v[1] = (uint32_t)(v >> 32);
+    return t.to_mont();
+}
+inline DFr root_of_unity() {  // halo2curves Fr::ROOT_OF_UNITY (Montgomery limbs)
+    DFr r;
+    const uint32_t v[8] = {0xb639feb8u, 0x9632c7c5u, 0x0d0ff299u, 0x985ce340u, 0x01b0ecd8u, 0xb2dd8800u, 0x6d98ce29u, 0x1d69070du};
+    for (int i = 0; i < 8; ++i) r.l.v[i] = v[i];
+    return r;
+}
+inline DFr zeta() {  // halo2curves Fr::ZETA
+    DFr z;
+    const uint32_t v[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu, 0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+    for (int i = 0; i < 8; ++i) z.l.v[i] = v[i];
+    return z;
+}
+}  // namespace detail
+
+// One context per process per GPU (B200ZK_DEVICE selects the ordinal); created on first use.
+class Backend {
+  public:
+    static Backend& get() {
+        static Backend b;
+        return b;
+    }
+    b200zk_ctx* ctx() const { return ctx_; }
+    void check(int32_t rc, const char* what) const {
+        if (rc != B200ZK_OK) throw Panic(std::string(what) + ": b200zk error " + std::to_string(rc) + ": " + b200zk_last_error(ctx_));
+    }
+
+  private:
+    Backend() {
+        int dev = 0;
+        if (const char* e = std::getenv("B200ZK_DEVICE")) dev = std::atoi(e);
+        if (b200zk_ctx_create(&dev, 1, &ctx_) != B200ZK_OK)
+            throw Panic("b200zk_ctx_create failed: no CUDA device (there is no CPU fallback)");
+    }
+    ~Backend() {
+        if (ctx_) b200zk_ctx_destroy(ctx_);
+    }
+    b200zk_ctx* ctx_ = nullptr;
+};
+
+namespace arithmetic {
+// pub fn best_multiexp<C: CurveAffine>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve
+inline G1 best_multiexp(const std::vector<Fr>& coeffs, const std::vector<G1Affine>& bases) {
+    if (coeffs.size() != bases.size()) throw Panic("assertion failed: `(left == right)` coeffs.len() == bases.len()");
+    G1 out;
+    auto& b = Backend::get();
+    b.check(b200zk_msm_g1_bases(b.ctx(), bases.data(), coeffs.data(), coeffs.size(), &out), "best_multiexp");
+    return out;
+}
+// pub fn best_fft<Scalar, G>(a: &mut [G], omega: Scalar, log_n: u32)      (G = Fr)
+inline void best_fft(std::vector<Fr>& a, const Fr& omega, uint32_t log_n) {
+    if (a.size() != (size_t(1) << log_n)) throw Panic("assertion failed: `(left == right)` a.len() == 1 << log_n");
+    auto& b = Backend::get();
+    b.check(b200zk_ntt_fr(b.ctx(), a.data(), log_n, &omega, 0, B200ZK_COSET_NONE), "best_fft");
+}
+inline Fr eval_polynomial(const std::vector<Fr>& poly, const Fr& point) {
+    Fr out;
+    auto& b = Backend::get();
+    b.check(b200zk_eval_poly(b.ctx(), poly.data(), poly.size(), &point, &out), "eval_polynomial");
+    return out;
+}
+inline std::vector<Fr> kate_division(const std::vector<Fr>& a, const Fr& bpt) {
+    if (a.empty()) throw Panic("attempt to subtract with overflow (a.len() - 1)");
+    std::vector<Fr> q(a.size() - 1);
+    auto& b = Backend::get();
+    b.check(b200zk_kate_division(b.ctx(), q.data(), a.data(), a.size(), &bpt), "kate_division");
+    return q;
+}
+}  // namespace arithmetic
+
+// halo2_proofs::poly::EvaluationDomain<Fr>
+class EvaluationDomain {
+  public:
+    uint32_t k, extended_k;
+    uint64_t n, quotient_poly_degree;
+    Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
+
+    // EvaluationDomain::new(j, k)
+    static EvaluationDomain new_(uint32_t j, uint32_t k) {
+        using detail::DFr;
+        EvaluationDomain d;
+        d.quotient_poly_degree = (uint64_t)j - 1;
+        d.n = 1ull << k;
+        d.k = k;
+        uint32_t ek = k;
+        while ((1ull << ek) < d.n * d.quotient_poly_degree) ek++;
+        if (ek > 28) throw Panic("assertion failed: extended_k <= Fr::S");
+        d.extended_k = ek;
+        DFr eo = detail::root_of_unity();
+        for (uint32_t i = ek; i < 28; ++i) eo = eo.sqr();
+        DFr om = eo;
+        for (uint32_t i = k; i < ek; ++i) om = om.sqr();
+        d.extended_omega = detail::from_dev(eo);
+        d.omega = detail::from_dev(om);
+        d.extended_omega_inv = detail::from_dev(eo.inv());
+        d.omega_inv = detail::from_dev(om.inv());
+        d.g_coset = detail::from_dev(detail::zeta());
+        d.g_coset_inv = detail::from_dev(detail::zeta().sqr());
+        d.ifft_divisor = detail::from_dev(detail::from_u64(1ull << k).inv());
+        d.extended_ifft_divisor = detail::from_dev(detail::from_u64(1ull << ek).inv());
+        return d;
+    }
+    // consumes and returns the polynomial like the Rust methods (moved in, moved out)
+    std::vector<Fr> lagrange_to_coeff(std::vector<Fr> a) const {
+        if (a.size() != n) throw Panic("assertion failed: a.values.len() == 1 << self.k");
+        auto& b = Backend::get();
+        b.check(b200zk_ntt_fr(b.ctx(), a.data(), k, &omega_inv, 1, B200ZK_COSET_NONE), "lagrange_to_coeff");
+        return a;
+    }
+    std::vector<Fr> coeff_to_extended(const std::vector<Fr>& a) const {
+        if (a.size() != n) throw Panic("assertion failed: a.values.len() == 1 << self.k");
+        std::vector<Fr> out(size_t(1) << extended_k);
+        auto& b = Backend::get();
+        b.check(b200zk_ntt_fr_ext(b.ctx(), a.data(), k, out.data(), extended_k, &extended_omega, 0, B200ZK_COSET_PRE), "coeff_to_extended");
+        return out;
+    }
+    std::vector<Fr> extended_to_coeff(std::vector<Fr> a) const {
+        if (a.size() != (size_t(1) << extended_k)) throw Panic("assertion failed: a.values.len() == self.extended_len()");
+        auto& b = Backend::get();
+        b.check(b200zk_ntt_fr(b.ctx(), a.data(), extended_k, &extended_omega_inv, 1, B200ZK_COSET_POST), "extended_to_coeff");
+        a.resize((size_t)(n * quotient_poly_degree));  // truncate to the quotient degree
+        return a;
+    }
+};
+
+// halo2_proofs::poly::kzg::commitment::ParamsKZG<Bn256>
+class ParamsKZG {
+  public:
+    uint32_t k = 0;
+    uint64_t n = 0;
+    std::vector<G1Affine> g, g_lagrange;
+    uint8_t g2[128] = {0}, s_g2[128] = {0};  // G2Affine RawBytes, carried opaquely (verification stays on the host)
+
+    ParamsKZG() = default;
+    ParamsKZG(const ParamsKZG&) = delete;
+    ParamsKZG& operator=(const ParamsKZG&) = delete;
+    ~ParamsKZG() { release(); }
+
+    // ParamsKZG::setup(k, rng) with a caller-provided s ("unsafe" test SRS): g[i] = s^i G; g_lagrange[i] = L_i(s) G
+    static void setup(ParamsKZG& p, uint32_t k, const Fr& s) {
+        using detail::DFr;
+        p.release();
+        p.k = k;
+        p.n = 1ull << k;
+        std::vector<Fr> sc(p.n);
+        DFr ds = detail::to_dev(s), cur = DFr::one();
+        for (uint64_t i = 0; i < p.n; ++i) {
+            sc[i] = detail::from_dev(cur);
+            cur = cur * ds;
+        }
+        auto& b = Backend::get();
+        p.g.resize(p.n);
+        b.check(b200zk_g1_generator_mul_batch(b.ctx(), sc.data(), p.n, p.g.data()), "setup(g)");
+        DFr root = detail::root_of_unity();
+        for (uint32_t i = k; i < 28; ++i) root = root.sqr();
+        DFr mult = (cur - DFr::one()) * detail::from_u64(p.n).inv();  // (s^n - 1) / n
+        DFr rp = DFr::one();
+        for (uint64_t i = 0; i < p.n; ++i) {
+            sc[i] = detail::from_dev(mult * rp * (ds - rp).inv());
+            rp = rp * root;
+        }
+        p.g_lagrange.resize(p.n);
+        b.check(b200zk_g1_generator_mul_batch(b.ctx(), sc.data(), p.n, p.g_lagrange.data()), "setup(g_lagrange)");
+    }
+
+    // SerdeFormat::RawBytes: k u32 LE | n x G1 (64 B) g | n x G1 g_lagrange | G2 g2 (128 B) | G2 s_g2 (128 B)
+    void write_custom(const std::string& path) const {
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) throw Panic("write_custom: cannot open " + path);
+        bool ok = std::fwrite(&k, 4, 1, f) == 1 && std::fwrite(g.data(), 64, n, f) == n && std::fwrite(g_lagrange.data(), 64, n, f) == n &&
+                  std::fwrite(g2, 128, 1, f) == 1 && std::fwrite(s_g2, 128, 1, f) == 1;
+        std::fclose(f);
+        if (!ok) throw Panic("write_custom: short write");
+    }
+    static void read_custom(ParamsKZG& p, const std::string& path) {
+        p.release();
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (!f) throw Panic("read_custom: cannot open " + path);
+        uint32_t k = 0;
+        bool ok = std::fread(&k, 4, 1, f) == 1 && k <= 28;
+        if (ok) {
+            p.k = k;
+            p.n = 1ull << k;
+            p.g.resize(p.n);
+            p.g_lagrange.resize(p.n);
+            ok = std::fread(p.g.data(), 64, p.n, f) == p.n && std::fread(p.g_lagrange.data(), 64, p.n, f) == p.n &&
+                 std::fread(p.g2, 128, 1, f) == 1 && std::fread(p.s_g2, 128, 1, f) == 1;
+        }
+        std::fclose(f);
+        if (!ok) throw Panic("read_custom: malformed params file " + path);
+    }
+
+    // ParamsProver::commit(poly, Blind): best_multiexp(poly, g[..poly.len()])   (blind ignored for KZG)
+    G1 commit(const std::vector<Fr>& poly) { return msm(dev_g_, g, B200ZK_SRS_G, poly); }
+    // Params::commit_lagrange(poly, Blind)
+    G1 commit_lagrange(const std::vector<Fr>& poly) { return msm(dev_gl_, g_lagrange, B200ZK_SRS_G_LAGRANGE, poly); }
+
+    void release() {
+        auto* c = Backend::get().ctx();
+        if (dev_g_) b200zk_srs_release(c, dev_g_);
+        if (dev_gl_) b200zk_srs_release(c, dev_gl_);
+        dev_g_ = dev_gl_ = nullptr;
+    }
+
+  private:
+    b200zk_srs *dev_g_ = nullptr, *dev_gl_ = nullptr;
+    G1 msm(b200zk_srs*& h, const std::vector<G1Affine>& bases, uint32_t tag, const std::vector<Fr>& poly) {
+        if (poly.size() > bases.size()) throw Panic("assertion failed: `(left == right)` coeffs.len() == bases.len()");
+        auto& b = Backend::get();
+        if (!h) b.check(b200zk_srs_register(b.ctx(), bases.data(), bases.size(), tag, &h), "srs_register");  // once, lazily
+        G1 out;
+        b.check(b200zk_msm_g1(b.ctx(), h, poly.data(), poly.size(), &out), "commit");
+        return out;
+    }
+};
+
+}  // namespace halo2_b200

@@ -1,0 +1,149 @@
+// GPU test of the C++ host mirror (scroll-prover_b200/halo2_b200.hpp) through the C ABI.
+// Mirrors the style of halo2_proofs' own unit tests: commit(p) == [p(s)] G on a test SRS, fft round trips,
+// coset extension round trip, params file round trip, panics on length mismatch.
+// Expected values come from the host emulation of ff.cuh / ec.cuh (double-and-add, Horner) -- a different
+// algorithm than the device Pippenger / NTT.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../scroll-prover_b200/halo2_b200.hpp"
+#include "../../scroll-prover_b200/csrc/ec.cuh"
+
+using namespace halo2_b200;
+using detail::DFr;
+
+#define REQUIRE(c)                                                     \
+    do {                                                               \
+        if (!(c)) {                                                    \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                  \
+        }                                                              \
+    } while (0)
+
+static uint64_t rng_state = 0x5EEDB2000001ull;
+static uint64_t xs() {
+    uint64_t x = rng_state;
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    rng_state = x;
+    return x * 0x2545F4914F6CDD1Dull;
+}
+static Fr rand_fr() {
+    Fr r{{xs(), xs(), xs(), xs() & 0x0fffffffffffffffull}};  // < 2^252 < r: valid Montgomery limbs
+    return r;
+}
+// [s] G by host double-and-add (s in Montgomery form), affine
+static G1Affine host_generator_mul(const Fr& s) {
+    b200zk::Fr c = detail::to_dev(s).from_mont();
+    b200zk::Fq gx = b200zk::Fq::one(), gy = b200zk::Fq::one().dbl();
+    b200zk::XYZZ acc = b200zk::XYZZ::identity();
+    for (int limb = 7; limb >= 0; --limb)
+        for (int b = 31; b >= 0; --b) {
+            acc = b200zk::xyzz_dbl(acc);
+            if ((c.l.v[limb] >> b) & 1) b200zk::xyzz_madd(acc, gx, gy);
+        }
+    b200zk::Affine a = b200zk::xyzz_to_affine(acc);
+    G1Affine out;
+    std::memcpy(&out, &a, 64);
+    return out;
+}
+static Fr host_eval(const std::vector<Fr>& p, const Fr& x) {
+    DFr acc = DFr::zero(), dx = detail::to_dev(x);
+    for (size_t i = p.size(); i-- > 0;) acc = acc * dx + detail::to_dev(p[i]);
+    return detail::from_dev(acc);
+}
+static bool same_point(const G1& j, const G1Affine& a) {  // device results are normalised (x, y, 1)
+    return std::memcmp(&j.x, &a.x, 32) == 0 && std::memcmp(&j.y, &a.y, 32) == 0 && !j.is_identity();
+}
+
+int main() {
+    const uint32_t k = 10;
+    const size_t n = size_t(1) << k;
+    EvaluationDomain dom = EvaluationDomain::new_(5, k);
+    REQUIRE(dom.extended_k == k + 2 && dom.quotient_poly_degree == 4);
+    REQUIRE(detail::from_dev(detail::to_dev(dom.omega).pow_u64(n)) == detail::from_dev(DFr::one()));
+    REQUIRE(detail::from_dev(detail::to_dev(dom.omega) * detail::to_dev(dom.omega_inv)) == detail::from_dev(DFr::one()));
+
+    ParamsKZG params;
+    Fr s = rand_fr();
+    ParamsKZG::setup(params, k, s);
+    REQUIRE(params.g.size() == n && params.g_lagrange.size() == n);
+    {
+        G1Affine g1 = host_generator_mul(s);  // g[1] = [s] G
+        REQUIRE(std::memcmp(&params.g[1], &g1, 64) == 0);
+    }
+    std::vector<Fr> poly(n);
+    for (auto& c : poly) c = rand_fr();
+    poly[0] = Fr{{0, 0, 0, 0}};
+
+    // commit(p) == [p(s)] G
+    G1 c1 = params.commit(poly);
+    Fr ps = host_eval(poly, s);
+    REQUIRE(arithmetic::eval_polynomial(poly, s) == ps);
+    REQUIRE(same_point(c1, host_generator_mul(ps)));
+
+    // commit_lagrange(evals) == commit(coeffs), evals = best_fft(coeffs, omega)
+    std::vector<Fr> evals = poly;
+    arithmetic::best_fft(evals, dom.omega, k);
+    G1 c2 = params.commit_lagrange(evals);
+    REQUIRE(std::memcmp(&c1, &c2, 96) == 0);
+    // A[1] = p(omega)
+    REQUIRE(evals[1] == host_eval(poly, dom.omega));
+
+    // lagrange_to_coeff inverts it
+    std::vector<Fr> back = dom.lagrange_to_coeff(evals);
+    REQUIRE(back == poly);
+
+    // coeff_to_extended: ext[i] = p(zeta * w_ext^i); extended_to_coeff returns the (zero-padded) coefficients
+    std::vector<Fr> ext = dom.coeff_to_extended(poly);
+    REQUIRE(ext.size() == 4 * n);
+    Fr pt = detail::from_dev(detail::to_dev(dom.g_coset) * detail::to_dev(dom.extended_omega).pow_u64(5));
+    REQUIRE(ext[5] == host_eval(poly, pt));
+    std::vector<Fr> coeffs4 = dom.extended_to_coeff(ext);
+    REQUIRE(coeffs4.size() == 4 * n);
+    for (size_t i = 0; i < n; ++i) REQUIRE(coeffs4[i] == poly[i]);
+    for (size_t i = n; i < 4 * n; ++i) REQUIRE((coeffs4[i].l[0] | coeffs4[i].l[1] | coeffs4[i].l[2] | coeffs4[i].l[3]) == 0);
+
+    // best_multiexp: generic bases, shorter slices, and the reference's length assertion
+    std::vector<Fr> sc(poly.begin(), poly.begin() + 100);
+    std::vector<G1Affine> bs(params.g.begin(), params.g.begin() + 100);
+    G1 m1 = arithmetic::best_multiexp(sc, bs);
+    G1 m2 = params.commit(sc);
+    REQUIRE(std::memcmp(&m1, &m2, 96) == 0);
+    bool panicked = false;
+    try {
+        bs.pop_back();
+        arithmetic::best_multiexp(sc, bs);
+    } catch (const Panic&) {
+        panicked = true;
+    }
+    REQUIRE(panicked);
+    panicked = false;
+    try {
+        std::vector<Fr> wrong(n / 2);
+        arithmetic::best_fft(wrong, dom.omega, k);
+    } catch (const Panic&) {
+        panicked = true;
+    }
+    REQUIRE(panicked);
+
+    // kate_division: a(X) - a(b) = q(X) (X - b)  => check at a random point
+    Fr bpt = rand_fr(), x = rand_fr();
+    std::vector<Fr> q = arithmetic::kate_division(poly, bpt);
+    DFr lhs = detail::to_dev(host_eval(poly, x)) - detail::to_dev(host_eval(poly, bpt));
+    DFr rhs = detail::to_dev(host_eval(q, x)) * (detail::to_dev(x) - detail::to_dev(bpt));
+    REQUIRE(detail::from_dev(lhs) == detail::from_dev(rhs));
+
+    // params file round trip (SerdeFormat::RawBytes layout)
+    const char* path = "/tmp/b200zk_params_test.bin";
+    params.write_custom(path);
+    ParamsKZG p2;
+    ParamsKZG::read_custom(p2, path);
+    REQUIRE(p2.k == k && p2.g.size() == n && std::memcmp(p2.g.data(), params.g.data(), 64 * n) == 0 &&
+            std::memcmp(p2.g_lagrange.data(), params.g_lagrange.data(), 64 * n) == 0);
+    G1 c3 = p2.commit(poly);
+    REQUIRE(std::memcmp(&c1, &c3, 96) == 0);
+    std::remove(path);
+
+    std::printf("ALL OK\n");
+    return 0;
+}
