@@ -118,6 +118,20 @@ def cpu_sample(k: int, threads: int, seed: int = 1):
     t0 = time.perf_counter(); O.best_multiexp(su, bases, threads); t["msm_u"] = time.perf_counter() - t0
     t0 = time.perf_counter(); coeff = dom.lagrange_to_coeff(su, threads); t["intt"] = time.perf_counter() - t0
     t0 = time.perf_counter(); dom.coeff_to_extended(coeff, threads); t["coset"] = time.perf_counter() - t0
+    # how many of the nominal host threads actually run in parallel (containers are often CPU-quota limited):
+    # one 2^13-point chunk alone vs one such chunk per thread, all at once
+    m = min(1 << 14, n)
+    reps = np.tile(su[:m], (threads, 1)); rb = np.tile(bases[:m], (threads, 1))
+    t1 = tT = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter(); O.best_multiexp(su[:m], bases[:m], 1); t1 = min(t1, time.perf_counter() - t0)
+        t0 = time.perf_counter(); O.best_multiexp(reps, rb, threads); tT = min(tT, time.perf_counter() - t0)
+    t["effective_parallelism"] = round(threads * t1 / tT, 1) if tT > 0 else None
+    t["affinity"] = len(os.sched_getaffinity(0))
+    for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        if os.path.exists(f):
+            t["cgroup_cpu"] = open(f).read().strip()
+            break
     step = (N_WITNESS_COLS * t["msm_w"] + (N_UNIFORM_COLS + N_COEFF_MSMS) * t["msm_u"]
             + (N_WITNESS_COLS + N_UNIFORM_COLS) * (t["intt"] + t["coset"]) + t["coset"])
     return step, t

@@ -85,13 +85,18 @@ __global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, 
 
 // counting-sort scatter in WINDOW-MAJOR order: concurrently running blocks work on the same window, so the
 // random 4-byte stores fall into one n*4-byte region that stays L2-resident (64 MiB at n = 2^24)
+// With a precomputed SRS (one bucket set) the destination of a digit is spread over the whole n*W*4-byte entry
+// array, so the kernel is run in SWEEPS over bucket ranges [b_lo, b_hi): each sweep re-reads the digits (coalesced)
+// but writes into a region small enough to stay L2-resident until its sectors are complete.
 __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ digits, uint64_t n, MsmPlan pl,
-                                                   uint32_t* cursor, uint32_t* entries) {
+                                                   uint32_t* cursor, uint32_t* entries, uint32_t b_lo, uint32_t b_hi) {
     uint64_t total = n * pl.W;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         uint32_t d = digits[idx];
         if (!d) continue;
+        uint32_t bk = (d & 0x7fffffffu) - 1;
+        if (bk < b_lo || bk >= b_hi) continue;
         uint64_t w = idx / n;
         uint32_t i = (uint32_t)(idx - w * n);
         uint32_t pos = atomicAdd(&cursor[(pl.Ws == 1 ? 0ull : w * pl.B) + (d & 0x7fffffffu) - 1], 1u);
@@ -599,7 +604,18 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             ProfScope ps_(ctx, PROF_MSM_SCATTER);
             uint64_t want = (max_entries + 1023) / 1024;  // 4 digits per thread, blocks issued in window-major order
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
-            msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries);
+            uint32_t sweeps = 1;
+            if (pl.Ws == 1) {
+                uint64_t region = 48ull << 20;  // bytes of the entry array written per sweep
+                sweeps = (uint32_t)((4 * max_entries + region - 1) / region);
+                if (sweeps < 1) sweeps = 1;
+                if (sweeps > 16) sweeps = 16;
+            }
+            for (uint32_t sw = 0; sw < sweeps; ++sw) {
+                uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sw / sweeps), b_hi = (uint32_t)((uint64_t)pl.B * (sw + 1) / sweeps);
+                msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries, b_lo, b_hi);
+                if (sw + 1 < sweeps) B2_LAUNCH_CHECK(ctx);
+            }
         }
         B2_LAUNCH_CHECK(ctx);
         uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
