@@ -71,6 +71,22 @@ def assign_jobs(jobs, world: int):
     return out
 
 
+def host_threads() -> int:
+    """Threads the reference's Rayon pool would get: min(logical CPUs, affinity mask, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 class ClockSampler:
     def __init__(self, device: int):
         self.device, self.rows, self.proc = device, [], None
@@ -141,7 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     vals = []
     for i in range(args.warmup + args.steps):
         step, detail = cpu_sample(args.k, threads, seed=1 + i)
@@ -249,42 +265,25 @@ def run_b200(args):
     # ---- e2e: host (pinned) columns -> session API; H2D of job j+1 overlaps compute of job j
     host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
             "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
-    stage = [torch.empty((n, 4), dtype=torch.int64, device=dev) for _ in range(2)]
     hstage = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev) if host["h"] is not None else None
     h2d_bytes = sum((1 << ek) * 32 if j[0] == "icoset" else n * 32 for j in my_jobs)
     d2h_bytes = n_msm * 96
 
+    col_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "column"]
+    msm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "msm"]
+    has_icoset = any(job[0] == "icoset" for job in my_jobs)
+
     def step_e2e():
-        used = [None, None]
-
-        def upload(j):
-            job = my_jobs[j]
-            with torch.cuda.stream(copy):
-                if job[0] == "icoset":
-                    hstage.copy_(host["h"], non_blocking=True)
-                    dst = hstage
-                else:
-                    b = j % 2
-                    if used[b] is not None:
-                        copy.wait_event(used[b])
-                    stage[b].copy_(host[job[1]][j % 2], non_blocking=True)
-                    dst = stage[b]
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            return dst, ev
-
-        nxt = upload(0) if my_jobs else None
-        mi = 0
-        for j, job in enumerate(my_jobs):
-            dst, ev = nxt
-            nxt = upload(j + 1) if j + 1 < len(my_jobs) else None
-            comp.wait_event(ev)
-            do_job(job, mi, dst)
-            if job[0] != "icoset":
-                mi += 1
-                e = torch.cuda.Event()
-                e.record(comp)
-                used[j % 2] = e
+        """Everything through the C ABI with HOST (pinned) buffers: b200zk_commit_columns double-buffers the H2D of
+        column j+1 on its copy stream against the kernels of column j; commitments are read back (D2H) per call."""
+        if col_jobs:
+            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in col_jobs], k, mode=2,
+                              omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)
+        if msm_jobs:
+            zk.commit_columns(ctx, params._g, [host[job[1]][j % 2] for j, job in msm_jobs], k, mode=0)
+        if has_icoset:
+            ctx.buf_upload(hstage, host["h"])
+            ctx.best_fft(hstage, dom.extended_omega_inv, ek, inverse_scale=True, coset_mode=zk.COSET_POST)
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -372,7 +371,7 @@ def run_b200(args):
         ntt_gbs = my_ntt_bytes * args.steps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             cs, detail = cpu_sample(k, threads)
             cpu = {"value": cs, "unit": "s", "cores": threads, "kind": "port",
                    "sample": "1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d on all host threads; step "
@@ -398,8 +397,9 @@ def run_b200(args):
             "kernel_ms_per_step_rank0": {c: prof[c]["ms"] / args.steps for c in prof if prof[c]["count"]},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "api": "ParamsKZG.commit_lagrange/commit + EvaluationDomain transforms on pinned host columns, "
-                           "double-buffered H2D on a copy stream (rank 0 bytes)"},
+                    "api": "C ABI with pinned HOST buffers: b200zk_commit_columns (mode 2 for the 28 columns, mode 0 for the 7 "
+                           "coefficient commits; H2D double-buffered on the library's copy stream), b200zk_buf_upload + "
+                           "b200zk_ntt_fr for the quotient (rank 0 bytes)"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_per_step": wall,
         }
         print(json.dumps(line))

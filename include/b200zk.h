@@ -98,6 +98,14 @@ B200ZK_API int32_t b200zk_g1_sum(b200zk_ctx* ctx, const void* jacobian_points, u
 /* out[i] = scalars[i] * G1 generator, affine (ParamsKZG::setup's g / g_lagrange generation) */
 B200ZK_API int32_t b200zk_g1_generator_mul_batch(b200zk_ctx* ctx, const void* scalars, uint64_t n, void* out_affine);
 
+/* ---- FFT over G1 (SRS tooling) --------------------------------------------------------------- */
+/* Replaces halo2_proofs::arithmetic::best_fft::<Fr, G1>(a, omega, log_n): in place on 2^log_n Jacobian points
+ * (96 B each, results normalised). */
+B200ZK_API int32_t b200zk_fft_g1(b200zk_ctx* ctx, void* jacobian_points, uint32_t log_n, const void* omega32);
+/* Replaces poly::kzg::commitment::g_to_lagrange(g, k) as used by Params::downsize
+ * (/root/reference/integration/tests/integration.rs:17-18): g_lagrange = iFFT_G1(g) / n, affine in, affine out. */
+B200ZK_API int32_t b200zk_g_to_lagrange(b200zk_ctx* ctx, const void* g_affine, uint32_t k, void* out_affine);
+
 /* ---- NTT ------------------------------------------------------------------------------------ */
 /* Replaces halo2_proofs::arithmetic::best_fft::<Fr, Fr>(a, omega, log_n) (arithmetic.rs @ e5ddf67):
  * in place, natural order in and out, a.len() == 1 << log_n, A[j] = sum_i a[i] omega^(ij).
@@ -109,6 +117,18 @@ B200ZK_API int32_t b200zk_ntt_fr(b200zk_ctx* ctx, void* data, uint32_t log_n, co
  * EvaluationDomain::coeff_to_extended == (log_in = k, log_n = extended_k, omega = extended_omega, PRE). */
 B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t log_in, void* out, uint32_t log_n,
                           const void* omega32, int inverse_scale, int coset_mode);
+
+/* ---- device-resident column pipeline (the per-column work of plonk::create_proof) ---------------- */
+/* For each of `count` columns of 2^k Lagrange values in HOST memory (pinned => the H2D copy of column j+1 overlaps the
+ * kernels of column j on an internal copy stream; pageable works too):
+ *   mode 0: commit_lagrange / commit only            (commits_out[j] = MSM over the first 2^k bases of `srs`)
+ *   mode 1: + lagrange_to_coeff   into coeff_out_dev[j] (device, 2^k elements)  or an internal scratch when NULL
+ *   mode 2: + coeff_to_extended   into ext_out_dev[j]   (device, 2^extended_k)  or an internal scratch when NULL
+ * commits_out: count x 96 B normalised Jacobian points (host or device).  No host synchronisation inside the loop;
+ * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs. */
+B200ZK_API int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count,
+                                         uint32_t k, const void* omega_inv32, const void* extended_omega32, uint32_t extended_k,
+                                         void* commits_out, void* const* coeff_out_dev, void* const* ext_out_dev, int mode);
 
 /* ---- polynomial batch ops (halo2_proofs Polynomial +,-,*scalar / parallelize loops) ---------- */
 B200ZK_API int32_t b200zk_poly_add(b200zk_ctx* ctx, void* r, const void* a, const void* b, uint64_t n);          /* r = a + b */

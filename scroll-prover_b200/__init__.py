@@ -75,8 +75,11 @@ def _load():
         "b200zk_msm_g1_bases": [vp, vp, vp, u64, vp],
         "b200zk_g1_sum": [vp, vp, u64, vp],
         "b200zk_g1_generator_mul_batch": [vp, vp, u64, vp],
+        "b200zk_fft_g1": [vp, vp, u32, vp],
+        "b200zk_g_to_lagrange": [vp, vp, u32, vp],
         "b200zk_ntt_fr": [vp, vp, u32, vp, C.c_int, C.c_int],
         "b200zk_ntt_fr_ext": [vp, vp, u32, vp, u32, vp, C.c_int, C.c_int],
+        "b200zk_commit_columns": [vp, vp, C.POINTER(vp), u32, u32, vp, vp, u32, vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
         "b200zk_poly_add": [vp, vp, vp, vp, u64],
         "b200zk_poly_sub": [vp, vp, vp, vp, u64],
         "b200zk_poly_mul": [vp, vp, vp, vp, u64],
@@ -106,7 +109,7 @@ ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
-    "b200zk_g1_generator_mul_batch", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_poly_add", "b200zk_poly_sub",
+    "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
@@ -179,6 +182,14 @@ class Context:
     def synchronize(self):
         self._ck(lib().b200zk_ctx_synchronize(self._h))
 
+    def buf_upload(self, dev, host):
+        """b200zk_buf_upload: host array / pinned tensor -> device tensor (H2D on the context stream, synchronous)."""
+        nbytes = _count(host, 1)
+        assert _count(dev, 1) >= nbytes
+        pd, k1 = _ptr(dev)
+        ph, k2 = _ptr(host)
+        self._ck(lib().b200zk_buf_upload(self._h, pd, ph, nbytes))
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         self._ck(lib().b200zk_ctx_launch_count(self._h, C.byref(v)))
@@ -245,6 +256,26 @@ class Context:
         ps, k1 = _ptr(scalars)
         po, k2 = _ptr(out)
         self._ck(lib().b200zk_g1_generator_mul_batch(self._h, ps, n, po))
+        return out
+
+    def best_fft_g1(self, jac_points, omega, log_n: int):
+        """arithmetic::best_fft::<Fr, G1> in place on (2^log_n, 12) Jacobian points."""
+        assert _count(jac_points, 96) == 1 << log_n
+        pa, k1 = _ptr(jac_points)
+        po, k2 = _ptr(omega)
+        self._ck(lib().b200zk_fft_g1(self._h, pa, log_n, po))
+        if not _is_torch(jac_points) and k1 is not jac_points:
+            jac_points[...] = k1.reshape(np.asarray(jac_points).shape)
+        return jac_points
+
+    def g_to_lagrange(self, g, k: int, out=None):
+        """poly::kzg::commitment::g_to_lagrange (Params::downsize): affine (2^k, 8) -> affine (2^k, 8)."""
+        assert _count(g, 64) == 1 << k
+        if out is None:
+            out = _like(g)
+        pg, k1 = _ptr(g)
+        po, k2 = _ptr(out)
+        self._ck(lib().b200zk_g_to_lagrange(self._h, pg, k, po))
         return out
 
     # ---- NTT
@@ -367,6 +398,29 @@ class Srs:
         if self._h:
             lib().b200zk_srs_release(self.ctx._h, self._h)
             self._h = C.c_void_p()
+
+
+def commit_columns(ctx: "Context", srs: "Srs", host_cols, k: int, mode: int = 0, omega_inv=None, extended_omega=None,
+                   extended_k: int = 0, coeff_out=None, ext_out=None) -> np.ndarray:
+    """b200zk_commit_columns: host columns (numpy arrays or pinned torch CPU tensors, 2^k x 4 u64 each) ->
+    (count, 12) commitments; mode 1/2 also runs lagrange_to_coeff / coeff_to_extended on the device."""
+    count = len(host_cols)
+    keep = [_ptr(c) for c in host_cols]
+    arr = (C.c_void_p * max(count, 1))(*[p for p, _ in keep])
+    out = np.zeros((count, 12), np.uint64)
+
+    def ptr_array(bufs):
+        if bufs is None:
+            return None, None
+        ks = [_ptr(b) for b in bufs]
+        return (C.c_void_p * max(count, 1))(*[p for p, _ in ks]), ks
+
+    ca, k1 = ptr_array(coeff_out)
+    ea, k2 = ptr_array(ext_out)
+    po, k3 = _ptr(omega_inv)
+    pe, k4 = _ptr(extended_omega)
+    ctx._ck(lib().b200zk_commit_columns(ctx._h, srs._h, arr, count, k, po, pe, extended_k, out.ctypes.data, ca, ea, mode))
+    return out
 
 
 class ParamsKZG:

@@ -16,6 +16,8 @@ int32_t poly_ew(b200zk_ctx* ctx, int op, Fr* r, const Fr* a, const Fr* b, const 
 int32_t eval_poly(b200zk_ctx* ctx, const Fr* poly, uint64_t n, const Fr& x, Fr* out_dev);
 int32_t batch_invert(b200zk_ctx* ctx, Fr* data, uint64_t n);
 int32_t kate_division(b200zk_ctx* ctx, Fr* q, const Fr* a, uint64_t n, const Fr& b);
+int32_t g1_fft_run(b200zk_ctx* ctx, const void* in, bool from_jac, void* out, bool to_jac, uint32_t log_n, const Fr& omega,
+                   const Fr* scale);
 int32_t field_op(b200zk_ctx* ctx, int field, int op, void* r, const void* a, const void* b, uint64_t n);
 }  // namespace b200zk
 
@@ -86,6 +88,13 @@ int32_t b200zk_ctx_destroy(b200zk_ctx* ctx) {
     for (auto& t : ctx->tables) cudaFree(t.dev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->msm_adds_dev) cudaFree(ctx->msm_adds_dev);
+    for (Scratch* s : {&ctx->colstage[0], &ctx->colstage[1], &ctx->col_coeff, &ctx->col_ext, &ctx->col_commits})
+        if (s->p) cudaFree(s->p);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B200ZK_OK;
@@ -288,6 +297,50 @@ int32_t b200zk_g1_generator_mul_batch(b200zk_ctx* ctx, const void* scalars, uint
     return B200ZK_OK;
 }
 
+// ---- FFT over G1 (SRS tooling) -------------------------------------------------------------------
+static int32_t g1_fft_common(b200zk_ctx* ctx, const void* in, bool from_jac, void* out, bool to_jac, uint32_t log_n,
+                             const Fr& omega, const Fr* scale) {
+    uint64_t n = 1ull << log_n;
+    size_t in_bytes = (from_jac ? sizeof(Jacobian) : sizeof(Affine)) * n, out_bytes = (to_jac ? sizeof(Jacobian) : sizeof(Affine)) * n;
+    const void* in_dev = nullptr;
+    B2_TRY(stage_in(ctx, ctx->stage_in, in, in_bytes, &in_dev));
+    bool out_is_dev = is_device_ptr(out);
+    void* out_dev = out;
+    if (!out_is_dev) {
+        B2_TRY(scratch_reserve(ctx, ctx->stage_out, out_bytes));
+        out_dev = ctx->stage_out.p;
+    }
+    B2_TRY(g1_fft_run(ctx, in_dev, from_jac, out_dev, to_jac, log_n, omega, scale));
+    if (!out_is_dev) return d2h(ctx, out, out_dev, out_bytes);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_fft_g1(b200zk_ctx* ctx, void* jacobian_points, uint32_t log_n, const void* omega32) {
+    CHECK_CTX(ctx);
+    if (!jacobian_points || !omega32 || log_n > 28) return fail(ctx, B200ZK_E_INVALID, "fft_g1: bad arguments");
+    Guard g(ctx);
+    Fr omega;
+    B2_TRY(read_fr(ctx, omega32, &omega));
+    return g1_fft_common(ctx, jacobian_points, true, jacobian_points, true, log_n, omega, nullptr);
+}
+
+int32_t b200zk_g_to_lagrange(b200zk_ctx* ctx, const void* g_affine, uint32_t k, void* out_affine) {
+    CHECK_CTX(ctx);
+    if (!g_affine || !out_affine || k > 28) return fail(ctx, B200ZK_E_INVALID, "g_to_lagrange: bad arguments");
+    Guard g(ctx);
+    // omega_inv = ROOT_OF_UNITY_INV^(2^(S-k)), n_inv = TWO_INV^k   (g_to_lagrange in poly/kzg/commitment.rs)
+    Fr root;
+    const uint32_t rv[8] = {0xb639feb8u, 0x9632c7c5u, 0x0d0ff299u, 0x985ce340u, 0x01b0ecd8u, 0xb2dd8800u, 0x6d98ce29u, 0x1d69070du};
+    for (int i = 0; i < 8; ++i) root.l.v[i] = rv[i];
+    for (uint32_t i = k; i < 28; ++i) root = root.sqr();
+    Fr omega_inv = root.inv();
+    Fr nf = Fr::zero();
+    nf.l.v[0] = (uint32_t)(1ull << k);
+    nf.l.v[1] = (uint32_t)((1ull << k) >> 32);
+    Fr n_inv = nf.to_mont().inv();
+    return g1_fft_common(ctx, g_affine, false, out_affine, false, k, omega_inv, &n_inv);
+}
+
 // ---- NTT ---------------------------------------------------------------------------------------
 int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t log_in, void* out, uint32_t log_n, const void* omega32,
                           int inverse_scale, int coset_mode) {
@@ -319,6 +372,74 @@ int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t log_in, void
 
 int32_t b200zk_ntt_fr(b200zk_ctx* ctx, void* data, uint32_t log_n, const void* omega32, int inverse_scale, int coset_mode) {
     return b200zk_ntt_fr_ext(ctx, data, log_n, data, log_n, omega32, inverse_scale, coset_mode);
+}
+
+// ---- device-resident column pipeline -------------------------------------------
+static int32_t pipeline_init(b200zk_ctx* ctx) {
+    if (ctx->copy_stream) return B200ZK_OK;
+    B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+    }
+    return B200ZK_OK;
+}
+
+// One call = the polynomial-arithmetic work create_proof does for `count` columns of 2^k Lagrange values held in
+// HOST memory (pinned for overlap): for each column  commit_lagrange -> lagrange_to_coeff -> (optional)
+// coeff_to_extended, with the H2D copy of column j+1 running on a copy stream while column j computes.
+int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count, uint32_t k,
+                              const void* omega_inv32, const void* extended_omega32, uint32_t extended_k, void* commits_out,
+                              void* const* coeff_out_dev, void* const* ext_out_dev, int mode) {
+    CHECK_CTX(ctx);
+    if (!srs || (count && (!host_cols || !commits_out)) || k > 28) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad arguments");
+    if (mode < 0 || mode > 2) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended)");
+    if (mode >= 1 && !omega_inv32) return fail(ctx, B200ZK_E_INVALID, "commit_columns: omega_inv required");
+    if (mode == 2 && (!extended_omega32 || extended_k < k || extended_k > 28)) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad extended domain");
+    uint64_t n = 1ull << k;
+    if (n > srs->n) return fail(ctx, B200ZK_E_INVALID, "commit_columns: 2^k exceeds the SRS length");
+    Guard g(ctx);
+    if (!count) return B200ZK_OK;
+    B2_TRY(pipeline_init(ctx));
+    Fr omega_inv = Fr::one(), ext_omega = Fr::one();
+    if (mode >= 1) B2_TRY(read_fr(ctx, omega_inv32, &omega_inv));
+    if (mode == 2) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
+    size_t col_bytes = sizeof(Fr) * n;
+    for (int i = 0; i < 2; ++i) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], col_bytes));
+    B2_TRY(scratch_reserve(ctx, ctx->col_commits, sizeof(Jacobian) * count));
+    if (mode >= 1) B2_TRY(scratch_reserve(ctx, ctx->col_coeff, col_bytes));
+    if (mode == 2) B2_TRY(scratch_reserve(ctx, ctx->col_ext, sizeof(Fr) << extended_k));
+    Jacobian* commits = (Jacobian*)ctx->col_commits.p;
+    bool used[2] = {false, false};
+    auto upload = [&](uint32_t j) -> int32_t {
+        int b = j & 1;
+        if (used[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
+        B2_CUDA(ctx, cudaMemcpyAsync(ctx->colstage[b].p, host_cols[j], col_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        return B200ZK_OK;
+    };
+    // the copy stream must not overtake work already queued on the compute stream that still reads the stage buffers
+    B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
+    B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+    B2_TRY(upload(0));
+    for (uint32_t j = 0; j < count; ++j) {
+        int b = j & 1;
+        if (j + 1 < count) B2_TRY(upload(j + 1));
+        B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        const Fr* col = (const Fr*)ctx->colstage[b].p;
+        B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, srs->pre_c, srs->n));
+        if (mode >= 1) {
+            Fr* coeff = (coeff_out_dev && coeff_out_dev[j]) ? (Fr*)coeff_out_dev[j] : (Fr*)ctx->col_coeff.p;
+            B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
+            if (mode == 2) {
+                Fr* ext = (ext_out_dev && ext_out_dev[j]) ? (Fr*)ext_out_dev[j] : (Fr*)ctx->col_ext.p;
+                B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
+            }
+        }
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], ctx->stream));
+        used[b] = true;
+    }
+    return deliver(ctx, commits_out, commits, sizeof(Jacobian) * count);
 }
 
 // ---- poly ops ------------------------------------------------------------------------------------

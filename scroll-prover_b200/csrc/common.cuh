@@ -60,6 +60,10 @@ struct b200zk_ctx {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<b200zk::TwiddleTable> tables;
+    // column pipeline (b200zk_commit_columns): copy stream + double-buffered staging
+    cudaStream_t copy_stream = nullptr;
+    b200zk::Scratch colstage[2], col_coeff, col_ext, col_commits;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     // profiling
     bool profiling = false;
     std::vector<b200zk::ProfSpan> prof_open;
@@ -68,6 +72,7 @@ struct b200zk_ctx {
     uint64_t prof_cnt[b200zk::PROF_NKEYS] = {0};
     // msm knobs / stats
     uint32_t msm_window = 0;
+    uint32_t msm_scatter_sweeps = 0;
     int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;
@@ -208,6 +213,7 @@ struct Guard {
 };
 
 // implemented in ntt.cu / msm.cu / poly.cu
+int32_t ntt_get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const Fr** out);
 int32_t ntt_run(b200zk_ctx* ctx, const Fr* in, uint32_t log_in, Fr* out, uint32_t log_n, const Fr& omega,
                 int inverse_scale, int coset_mode);
 

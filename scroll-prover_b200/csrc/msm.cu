@@ -606,10 +606,9 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
             uint32_t sweeps = 1;
             if (pl.Ws == 1) {
-                uint64_t region = 48ull << 20;  // bytes of the entry array written per sweep
-                sweeps = (uint32_t)((4 * max_entries + region - 1) / region);
-                if (sweeps < 1) sweeps = 1;
-                if (sweeps > 16) sweeps = 16;
+                // measured on B200 (profiles/): re-reading the digits once per sweep costs more than the L2 locality
+                // buys (16 sweeps: 6.3 -> ~18 ms at 2^24), so a single sweep is used; the knob stays for experiments
+                sweeps = ctx->msm_scatter_sweeps ? ctx->msm_scatter_sweeps : 1;
             }
             for (uint32_t sw = 0; sw < sweeps; ++sw) {
                 uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sw / sweeps), b_hi = (uint32_t)((uint64_t)pl.B * (sw + 1) / sweeps);

@@ -295,7 +295,7 @@ static Fr host_zeta() {  // halo2curves Fr::ZETA in Montgomery form
     return z;
 }
 
-static int32_t get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const Fr** out) {
+int32_t ntt_get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const Fr** out) {
     // level roots w[u] = omega^(2^(log_n-u)); validate primitivity
     LevelRoots roots;
     roots.w[log_n] = omega;
@@ -393,7 +393,7 @@ int32_t ntt_run(b200zk_ctx* ctx, const Fr* in, uint32_t log_in, Fr* out, uint32_
         return B200ZK_OK;
     }
     const Fr* tab = nullptr;
-    B2_TRY(get_table(ctx, omega, log_n, &tab));
+    B2_TRY(ntt_get_table(ctx, omega, log_n, &tab));
 
     Fr zeta = host_zeta(), zeta2 = zeta.sqr();
     Fr3 pre_c, post_c;

@@ -299,6 +299,23 @@ def test_large_msm_properties(ctx, zk):
     srs.release()
 
 
+# --------------------------------------------------------------------------- FFT over G1 (Params::downsize)
+@pytest.mark.parametrize("k", [1, 4, 8])
+def test_g_to_lagrange_and_fft_g1_match_oracle(ctx, k):
+    n = 1 << k
+    tau = O.fr_from_int(0xB200_5EED_0009)
+    g, gl = O.params_setup(k, tau, threads=8)
+    got = ctx.g_to_lagrange(g, k)
+    assert np.array_equal(got, gl)  # == oracle's setup-time g_lagrange == O.g_to_lagrange(g)
+    # generic best_fft over projective points with the forward root
+    w = omega_for(k)
+    jac = np.stack([O.g1_from_affine(p) for p in g])
+    exp = O.best_fft_g1(jac, w, k, threads=4)
+    out = jac.copy()
+    ctx.best_fft_g1(out, w, k)
+    assert np.array_equal(np.stack([norm_affine(p) for p in out]), np.stack([norm_affine(p) for p in exp]))
+
+
 # --------------------------------------------------------------------------- poly batch ops
 @pytest.mark.parametrize("n", [1, 5, 1000, (1 << 16) + 3])
 def test_poly_ops_match_oracle(ctx, n):
@@ -320,6 +337,34 @@ def test_poly_ops_match_oracle(ctx, n):
     inv = b.copy()
     ctx.batch_invert(inv)
     assert np.array_equal(inv, O.fr_batch_invert(b))
+
+
+def test_commit_columns_pipeline_matches_oracle(ctx, zk):
+    """b200zk_commit_columns (host columns, internal double-buffered H2D): commitments, coefficients and extended
+    evaluations of every column equal the oracle's commit_lagrange / lagrange_to_coeff / coeff_to_extended."""
+    import torch
+
+    k = 10
+    n = 1 << k
+    g = O.fill_points_chain(n, 91, 8)
+    srs = ctx.srs_register(g, zk.SRS_G_LAGRANGE)
+    dom, dom_o = zk.EvaluationDomain(ctx, 5, k), O.EvaluationDomain(5, k)
+    cols = [O.fill_fr(n, SEED + 900 + i, witness_like=(i % 2 == 0)) for i in range(5)]
+    pinned = [torch.from_numpy(c.view(np.int64)).pin_memory() for c in cols[:3]] + cols[3:]  # pinned and pageable
+    coeff_out = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in cols]
+    ext_out = [torch.empty((4 * n, 4), dtype=torch.int64, device="cuda") for _ in cols]
+    torch.cuda.synchronize()
+    commits = zk.commit_columns(ctx, srs, pinned, k, mode=2, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
+                                extended_k=k + 2, coeff_out=coeff_out, ext_out=ext_out)
+    ctx.synchronize()
+    for i, c in enumerate(cols):
+        assert np.array_equal(norm_affine(commits[i]), norm_affine(O.best_multiexp(c, g, threads=4))), i
+        ce = dom_o.lagrange_to_coeff(c, threads=4)
+        assert np.array_equal(coeff_out[i].cpu().numpy().view(np.uint64), ce), i
+        assert np.array_equal(ext_out[i].cpu().numpy().view(np.uint64), dom_o.coeff_to_extended(ce, threads=4)), i
+    only = zk.commit_columns(ctx, srs, cols, k, mode=0)
+    assert np.array_equal(only, commits)
+    srs.release()
 
 
 def test_device_resident_buffers(ctx, zk):
