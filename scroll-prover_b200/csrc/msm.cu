@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restr
 // ~100 dependent point additions and ~200 dependent doublings; this has ~40 additions and kc doublings):
 // view the set as a matrix i = hi*2^kc + lo;  Row_hi = sum_lo B, Col_lo = sum_hi B   (block tree sums), then
 //   S = WS(Col) + 2^kc * WS(Row) + sum(Row),     WS(V) = sum_j j V_j = sum_{j>=1} Suffix_j(V)   (parallel suffix scan).
-static constexpr int RED_T = 256;
+static constexpr int RED_T = 128;   // 4 blocks/SM at 128 registers: the sums are latency-bound, more blocks in flight win
 
 __device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {  // result valid in thread 0
     st_xyzz(sh + threadIdx.x, v);
@@ -365,7 +365,7 @@ __device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {  // result v
 }
 
 // grid = (rows + cols, Ws); block j < rows sums row j, block rows + j sums column j.  vec[set][0..rows) | [rows..rows+cols)
-__global__ void __launch_bounds__(RED_T) msm_rowcol_sums(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t kc, XYZZ* __restrict__ vec) {
+__global__ void __launch_bounds__(RED_T, 4) msm_rowcol_sums(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t kc, XYZZ* __restrict__ vec) {
     __shared__ XYZZ sh[RED_T];
     const uint32_t cols = 1u << kc, rows = B >> kc;
     const XYZZ* bk = buckets + (uint64_t)blockIdx.y * B;

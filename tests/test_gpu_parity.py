@@ -386,3 +386,47 @@ def test_device_resident_buffers(ctx, zk):
     back = dom.extended_to_coeff(ext)
     ctx.synchronize()
     assert np.array_equal(back.cpu().numpy().view(np.uint64)[: 1 << k], coeff_exp)
+
+
+# --------------------------------------------------------------------------- BASELINE full sizes (properties)
+def test_full_size_degree24_column(ctx, zk):
+    """configs[1] sizes: one 2^24 column through commit_lagrange -> lagrange_to_coeff -> coeff_to_extended (2^26) ->
+    extended_to_coeff, checked by size-independent properties against the oracle (inner product, Horner evaluation,
+    round trips)."""
+    import torch
+
+    k = 24
+    n = 1 << k
+    dom = zk.EvaluationDomain(ctx, 5, k)
+    # SRS with known discrete logs: g[i] = s_i G  =>  MSM(a, g) = <a, s> G
+    s_host = O.fill_fr(n, SEED + 1000)
+    g_dev = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.g1_generator_mul_batch(s_host, out=g_dev)
+    srs = ctx.srs_register(g_dev)
+    del g_dev
+    a = O.fill_fr(n, SEED + 1001, witness_like=True)
+    a[5::7] = O.fill_fr(len(a[5::7]), SEED + 1002)  # mix in uniform scalars
+    G = O.g1_from_affine(O.g1_generator())
+    got = srs.msm(a)
+    assert np.array_equal(norm_affine(got), norm_affine(O.g1_mul(G, O.compute_inner_product(a, s_host))))
+    srs.release()
+    # lagrange_to_coeff on the device-resident column, then the coset extension
+    col = torch.from_numpy(a.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    dom.lagrange_to_coeff(col)
+    ext = dom.coeff_to_extended(col)
+    ctx.synchronize()
+    coeff = col.cpu().numpy().view(np.uint64)
+    # a[j] = p(omega^j) for the recovered coefficients
+    for j in (0, 1, n - 1):
+        assert np.array_equal(O.eval_polynomial(coeff, O.fr_pow_u64(dom.omega, j)), a[j])
+    # ext[j] = p(zeta * w_ext^j)
+    exth = ext.cpu().numpy().view(np.uint64)
+    for j in (0, 3, (1 << 26) - 1):
+        x = O.fr_mul(dom.g_coset, O.fr_pow_u64(dom.extended_omega, j))
+        assert np.array_equal(exth[j], O.eval_polynomial(coeff, x))
+    back = dom.extended_to_coeff(ext)
+    ctx.synchronize()
+    backh = back.cpu().numpy().view(np.uint64)
+    assert np.array_equal(backh[:n], coeff) and not backh[n:].any()
