@@ -430,3 +430,30 @@ def test_full_size_degree24_column(ctx, zk):
     ctx.synchronize()
     backh = back.cpu().numpy().view(np.uint64)
     assert np.array_equal(backh[:n], coeff) and not backh[n:].any()
+
+
+def test_max_size_ntt_2_28(ctx, zk):
+    """Largest transform the field supports (Fr two-adicity S = 28, the extended domain of a k = 26 layer): 8 GiB
+    vector, 4 passes.  Device round trip must be bit-exact and X[1] = p(omega) must match the oracle's Horner."""
+    import torch
+
+    log_n = 28
+    n = 1 << log_n
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip("needs ~40 GiB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(28)
+    a = torch.randint(-(2 ** 63), 2 ** 63 - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+    a[:, 3] &= 0x0FFFFFFFFFFFFFFF
+    ref = a.clone()
+    w = omega_for(log_n)
+    torch.cuda.synchronize()
+    ctx.best_fft(a, w, log_n)
+    ctx.synchronize()
+    x1 = a[1].cpu().numpy().view(np.uint64)
+    host = ref.cpu().numpy().view(np.uint64)
+    assert np.array_equal(x1, O.eval_polynomial(host, w))
+    del host
+    ctx.best_fft(a, O.fr_inv(w), log_n, inverse_scale=True)
+    ctx.synchronize()
+    assert torch.equal(a, ref)
