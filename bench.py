@@ -54,8 +54,11 @@ def workload_desc(k: int) -> str:
 
 def make_jobs():
     """(kind, scalar distribution, relative cost) for every independent unit of the step."""
-    jobs = [("column", "w", 1.0)] * N_WITNESS_COLS + [("column", "u", 1.3)] * N_UNIFORM_COLS
-    jobs += [("msm", "u", 0.9)] * N_COEFF_MSMS + [("icoset", "u", 0.35)]
+    # A column's commitment (MSM) and its transforms (iNTT + coset NTT) are independent, so they are separate jobs.
+    # relative costs measured on B200 at k = 24 (ms): witness-like MSM 11, uniform MSM 44, transform chain 18, icoset 16
+    jobs = [("lmsm", "w", 11.0)] * N_WITNESS_COLS + [("lmsm", "u", 44.0)] * N_UNIFORM_COLS   # commit_lagrange
+    jobs += [("ntt", "w", 18.0)] * N_WITNESS_COLS + [("ntt", "u", 18.0)] * N_UNIFORM_COLS      # lagrange_to_coeff + coeff_to_extended
+    jobs += [("msm", "u", 44.0)] * N_COEFF_MSMS + [("icoset", "u", 16.0)]
     return jobs
 
 
@@ -237,14 +240,15 @@ def run_b200(args):
     ext = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev)
     hwork = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev)
     my_jobs = assign_jobs(make_jobs(), world)[rank]
-    n_msm = sum(1 for j in my_jobs if j[0] in ("column", "msm"))
+    n_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
     commits = np.zeros((max(n_msm, 1), 12), np.uint64)
     msm_units = {"adds": 0, "nw": 0}
 
     def do_job(job, idx, src):
         kind = job[0]
-        if kind == "column":
+        if kind == "lmsm":
             commits[idx] = params.commit_lagrange(src)
+        elif kind == "ntt":
             ctx.ntt_ext(src, k, coeff, k, dom.omega_inv, True, zk.COSET_NONE)
             ctx.ntt_ext(coeff, k, ext, ek, dom.extended_omega, False, zk.COSET_PRE)
         elif kind == "msm":
@@ -259,25 +263,36 @@ def run_b200(args):
         mi = 0
         for j, job in enumerate(my_jobs):
             do_job(job, mi, src_for(job, j))
-            if job[0] != "icoset":
+            if job[0] in ("lmsm", "msm"):
                 mi += 1
 
     # ---- e2e: host (pinned) columns -> session API; H2D of job j+1 overlaps compute of job j
     host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
             "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
     hstage = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev) if host["h"] is not None else None
-    h2d_bytes = sum((1 << ek) * 32 if j[0] == "icoset" else n * 32 for j in my_jobs)
+    if world == 1:  # every column crosses PCIe once (commitment + transforms in one mode-2 call)
+        h2d_bytes = (N_WITNESS_COLS + N_UNIFORM_COLS + N_COEFF_MSMS) * n * 32 + (1 << ek) * 32
+    else:
+        h2d_bytes = sum((1 << ek) * 32 if j[0] == "icoset" else n * 32 for j in my_jobs)
     d2h_bytes = n_msm * 96
 
-    col_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "column"]
+    lmsm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "lmsm"]
+    ntt_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "ntt"]
     msm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "msm"]
     has_icoset = any(job[0] == "icoset" for job in my_jobs)
 
     def step_e2e():
         """Everything through the C ABI with HOST (pinned) buffers: b200zk_commit_columns double-buffers the H2D of
         column j+1 on its copy stream against the kernels of column j; commitments are read back (D2H) per call."""
-        if col_jobs:
-            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in col_jobs], k, mode=2,
+        # a column whose commitment and transforms both landed on this rank is uploaded once (mode 2)
+        both = min(len(lmsm_jobs), len(ntt_jobs)) if world == 1 else 0
+        if both:
+            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in lmsm_jobs[:both]], k, mode=2,
+                              omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)
+        if lmsm_jobs[both:]:
+            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in lmsm_jobs[both:]], k, mode=0)
+        if ntt_jobs[both:]:
+            zk.commit_columns(ctx, None, [host[job[1]][j % 2] for j, job in ntt_jobs[both:]], k, mode=3,
                               omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)
         if msm_jobs:
             zk.commit_columns(ctx, params._g, [host[job[1]][j % 2] for j, job in msm_jobs], k, mode=0)
@@ -351,15 +366,15 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        my_msm = sum(1 for j in my_jobs if j[0] != "icoset")
+        my_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
         actual_adds = prof.pop("_actual_adds")
         msm_ms = sum(prof[c]["ms"] for c in prof if c.startswith("msm_"))
         acc_ms, acc_cnt = prof["msm_accumulate"]["ms"], prof["msm_accumulate"]["count"]
         ntt_ms, ntt_cnt = prof["ntt_pass"]["ms"], prof["ntt_pass"]["count"]
-        my_bf = sum(bf(k) + bf(ek) for j in my_jobs if j[0] == "column") + sum(bf(ek) for j in my_jobs if j[0] == "icoset")
+        my_bf = sum(bf(k) + bf(ek) for j in my_jobs if j[0] == "ntt") + sum(bf(ek) for j in my_jobs if j[0] == "icoset")
         my_ntt_bytes = 0
         for j in my_jobs:  # algorithmic HBM bytes: 64 B/element/pass, P = ceil(log_n / 8) passes in this build
-            if j[0] == "column":
+            if j[0] == "ntt":
                 my_ntt_bytes += 64 * n * 3 + 64 * (1 << ek) * 4
             elif j[0] == "icoset":
                 my_ntt_bytes += 64 * (1 << ek) * 4

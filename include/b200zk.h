@@ -124,6 +124,8 @@ B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t l
  *   mode 0: commit_lagrange / commit only            (commits_out[j] = MSM over the first 2^k bases of `srs`)
  *   mode 1: + lagrange_to_coeff   into coeff_out_dev[j] (device, 2^k elements)  or an internal scratch when NULL
  *   mode 2: + coeff_to_extended   into ext_out_dev[j]   (device, 2^extended_k)  or an internal scratch when NULL
+ *   mode 3: lagrange_to_coeff + coeff_to_extended only (no commitment; srs and commits_out may be NULL) -- lets a
+ *           multi-GPU caller place a column's MSM and its transforms on different ranks
  * commits_out: count x 96 B normalised Jacobian points (host or device).  No host synchronisation inside the loop;
  * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs. */
 B200ZK_API int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count,

@@ -419,7 +419,8 @@ def commit_columns(ctx: "Context", srs: "Srs", host_cols, k: int, mode: int = 0,
     ea, k2 = ptr_array(ext_out)
     po, k3 = _ptr(omega_inv)
     pe, k4 = _ptr(extended_omega)
-    ctx._ck(lib().b200zk_commit_columns(ctx._h, srs._h, arr, count, k, po, pe, extended_k, out.ctypes.data, ca, ea, mode))
+    ctx._ck(lib().b200zk_commit_columns(ctx._h, srs._h if srs is not None else None, arr, count, k, po, pe, extended_k,
+                                        out.ctypes.data, ca, ea, mode))
     return out
 
 

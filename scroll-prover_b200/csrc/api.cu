@@ -395,23 +395,25 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
                               const void* omega_inv32, const void* extended_omega32, uint32_t extended_k, void* commits_out,
                               void* const* coeff_out_dev, void* const* ext_out_dev, int mode) {
     CHECK_CTX(ctx);
-    if (!srs || (count && (!host_cols || !commits_out)) || k > 28) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad arguments");
-    if (mode < 0 || mode > 2) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended)");
+    if ((mode != 3 && !srs) || (count && (!host_cols || (mode != 3 && !commits_out))) || k > 28)
+        return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad arguments");
+    if (mode < 0 || mode > 3) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended), 3 (coeff+extended only)");
+    const bool do_commit = mode != 3, do_ext = mode >= 2;
     if (mode >= 1 && !omega_inv32) return fail(ctx, B200ZK_E_INVALID, "commit_columns: omega_inv required");
-    if (mode == 2 && (!extended_omega32 || extended_k < k || extended_k > 28)) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad extended domain");
+    if (mode >= 2 && (!extended_omega32 || extended_k < k || extended_k > 28)) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad extended domain");
     uint64_t n = 1ull << k;
-    if (n > srs->n) return fail(ctx, B200ZK_E_INVALID, "commit_columns: 2^k exceeds the SRS length");
+    if (mode != 3 && n > srs->n) return fail(ctx, B200ZK_E_INVALID, "commit_columns: 2^k exceeds the SRS length");
     Guard g(ctx);
     if (!count) return B200ZK_OK;
     B2_TRY(pipeline_init(ctx));
     Fr omega_inv = Fr::one(), ext_omega = Fr::one();
     if (mode >= 1) B2_TRY(read_fr(ctx, omega_inv32, &omega_inv));
-    if (mode == 2) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
+    if (mode >= 2) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
     size_t col_bytes = sizeof(Fr) * n;
     for (int i = 0; i < 2; ++i) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], col_bytes));
     B2_TRY(scratch_reserve(ctx, ctx->col_commits, sizeof(Jacobian) * count));
     if (mode >= 1) B2_TRY(scratch_reserve(ctx, ctx->col_coeff, col_bytes));
-    if (mode == 2) B2_TRY(scratch_reserve(ctx, ctx->col_ext, sizeof(Fr) << extended_k));
+    if (do_ext) B2_TRY(scratch_reserve(ctx, ctx->col_ext, sizeof(Fr) << extended_k));
     Jacobian* commits = (Jacobian*)ctx->col_commits.p;
     bool used[2] = {false, false};
     auto upload = [&](uint32_t j) -> int32_t {
@@ -430,11 +432,11 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
         if (j + 1 < count) B2_TRY(upload(j + 1));
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
         const Fr* col = (const Fr*)ctx->colstage[b].p;
-        B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, srs->pre_c, srs->n));
+        if (do_commit) B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, srs->pre_c, srs->n));
         if (mode >= 1) {
             Fr* coeff = (coeff_out_dev && coeff_out_dev[j]) ? (Fr*)coeff_out_dev[j] : (Fr*)ctx->col_coeff.p;
             B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
-            if (mode == 2) {
+            if (do_ext) {
                 Fr* ext = (ext_out_dev && ext_out_dev[j]) ? (Fr*)ext_out_dev[j] : (Fr*)ctx->col_ext.p;
                 B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
             }
@@ -442,6 +444,7 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], ctx->stream));
         used[b] = true;
     }
+    if (!do_commit) return B200ZK_OK;
     return deliver(ctx, commits_out, commits, sizeof(Jacobian) * count);
 }
 

@@ -606,9 +606,13 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
             uint32_t sweeps = 1;
             if (pl.Ws == 1) {
-                // measured on B200 (profiles/): re-reading the digits once per sweep costs more than the L2 locality
-                // buys (16 sweeps: 6.3 -> ~18 ms at 2^24), so a single sweep is used; the knob stays for experiments
-                sweeps = ctx->msm_scatter_sweeps ? ctx->msm_scatter_sweeps : 1;
+                // measured on B200 at n = 2^24 (805 MB of entries): 1 sweep 6.3 ms, 2: 4.9, 4: 4.1, 16: 11.5 -- each sweep
+                // re-reads the digits, so only a few sweeps of ~200 MB pay off
+                uint64_t region = 200ull << 20;
+                sweeps = (uint32_t)((4 * max_entries + region - 1) / region);
+                if (sweeps < 1) sweeps = 1;
+                if (sweeps > 4) sweeps = 4;
+                if (ctx->msm_scatter_sweeps) sweeps = ctx->msm_scatter_sweeps;
             }
             for (uint32_t sw = 0; sw < sweeps; ++sw) {
                 uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sw / sweeps), b_hi = (uint32_t)((uint64_t)pl.B * (sw + 1) / sweeps);

@@ -76,9 +76,9 @@ def test_job_fanout_is_balanced_and_complete():
     import bench
 
     jobs = bench.make_jobs()
-    assert len(jobs) == 36 and sum(1 for j in jobs if j[0] in ("column", "msm")) == 35
+    assert sum(1 for j in jobs if j[0] in ("lmsm", "msm")) == 35 and sum(1 for j in jobs if j[0] == "ntt") == 28
     for world in (1, 2, 4, 8):
         parts = bench.assign_jobs(jobs, world)
         assert sum(len(p) for p in parts) == len(jobs)
         loads = [sum(j[2] for j in p) for p in parts]
-        assert max(loads) <= sum(loads) / world + 1.3  # within one job of perfect balance
+        assert max(loads) <= sum(loads) / world + 44.0  # within one job of perfect balance
