@@ -89,7 +89,18 @@ __global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, 
 // array, so the kernel is run in SWEEPS over bucket ranges [b_lo, b_hi): each sweep re-reads the digits (coalesced)
 // but writes into a region small enough to stay L2-resident until its sectors are complete.
 __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ digits, uint64_t n, MsmPlan pl,
-                                                   uint32_t* cursor, uint32_t* entries, uint32_t b_lo, uint32_t b_hi) {
+                                                   uint32_t* cursor, uint32_t* entries, const uint32_t* __restrict__ total_entries,
+                                                   uint32_t sweep, uint32_t max_sweeps) {
+    // the number of sweeps actually used follows the real entry count M (known only on the device): sparse
+    // witness columns have few entries and get a single sweep
+    uint32_t eff = 1;
+    if (max_sweeps > 1) {
+        uint64_t bytes = 4ull * (*total_entries);
+        eff = (uint32_t)((bytes + (200ull << 20) - 1) / (200ull << 20));
+        eff = eff < 1 ? 1 : (eff > max_sweeps ? max_sweeps : eff);
+    }
+    if (sweep >= eff) return;
+    const uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sweep / eff), b_hi = (uint32_t)((uint64_t)pl.B * (sweep + 1) / eff);
     uint64_t total = n * pl.W;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -615,8 +626,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
                 if (ctx->msm_scatter_sweeps) sweeps = ctx->msm_scatter_sweeps;
             }
             for (uint32_t sw = 0; sw < sweeps; ++sw) {
-                uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sw / sweeps), b_hi = (uint32_t)((uint64_t)pl.B * (sw + 1) / sweeps);
-                msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries, b_lo, b_hi);
+                msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries, offsets + pl.NB, sw, sweeps);
                 if (sw + 1 < sweeps) B2_LAUNCH_CHECK(ctx);
             }
         }
