@@ -220,7 +220,7 @@ __device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
 __global__ void __launch_bounds__(256, 2)
 msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                uint64_t NB, XYZZ* __restrict__ buckets, uint32_t* __restrict__ part_id, XYZZ* __restrict__ part_val,
-               uint64_t nthreads) {
+               uint64_t nthreads, uint32_t* __restrict__ giant_flag) {
     uint64_t tau = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tau >= nthreads) return;
     const uint32_t M = offsets[NB];
@@ -248,6 +248,7 @@ msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ en
                 st_xyzz(buckets + b, acc);
             } else {
                 uint32_t giant = (bucket_end - bucket_start > BIG_BUCKET) ? PART_GIANT : 0u;
+                if (giant) *giant_flag = 1u;  // benign race: every writer stores the same value
                 part_id[2 * tau + slot] = b | giant | (run_starts ? PART_STARTS : 0u) | (run_ends ? PART_ENDS : 0u);
                 st_xyzz(part_val + 2 * tau + slot, acc);
                 ++slot;
@@ -295,7 +296,9 @@ __global__ void __launch_bounds__(128) msm_combine_heads(const uint32_t* __restr
 static constexpr int COMBINE_LR = 64;
 __global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restrict__ in_id, const XYZZ* __restrict__ in_val,
                                                          uint64_t nrec, XYZZ* __restrict__ buckets, uint32_t* __restrict__ out_id,
-                                                         XYZZ* __restrict__ out_val, uint64_t nthreads) {
+                                                         XYZZ* __restrict__ out_val, uint64_t nthreads,
+                                                         const uint32_t* __restrict__ giant_flag) {
+    if (*giant_flag == 0) return;  // no giant bucket in this MSM (the common case): nothing to reduce
     uint64_t sigma = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sigma >= nthreads) return;
     out_id[2 * sigma] = PART_INVALID;
@@ -336,7 +339,8 @@ __global__ void __launch_bounds__(128) msm_combine_level(const uint32_t* __restr
 
 // last level (few records): the head record of every giant bucket sums forward to the record that ends it
 __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restrict__ part_id, const XYZZ* __restrict__ part_val,
-                                                         uint64_t nrec, XYZZ* __restrict__ buckets) {
+                                                         uint64_t nrec, XYZZ* __restrict__ buckets, const uint32_t* __restrict__ giant_flag) {
+    if (*giant_flag == 0) return;
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
     uint32_t id = part_id[r];
@@ -561,6 +565,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_hist = carve(4 * (pl.NB + 1)), o_offs = carve(4 * (pl.NB + 1)), o_cursor = carve(4 * (pl.NB + 1));
     size_t o_tiles = carve(4 * (size_t)(ntiles + 1));
+    size_t o_flag = carve(256);
     size_t o_entries = carve(4 * (max_entries + 4));
     size_t o_digits = carve(4 * (max_entries + 4));
     size_t o_buckets = carve(sizeof(XYZZ) * pl.NB);
@@ -577,6 +582,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     uint32_t* offsets = (uint32_t*)(base + o_offs);
     uint32_t* cursor = (uint32_t*)(base + o_cursor);
     uint32_t* tiles = (uint32_t*)(base + o_tiles);
+    uint32_t* giant_flag = (uint32_t*)(base + o_flag);
     uint32_t* entries = (uint32_t*)(base + o_entries);
     uint32_t* digits = (uint32_t*)(base + o_digits);
     uint32_t* pid2 = (uint32_t*)(base + o_pid2);
@@ -590,6 +596,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
 
     cudaStream_t st = ctx->stream;
     B2_CUDA(ctx, cudaMemsetAsync(hist, 0, 4 * (pl.NB + 1), st));
+    B2_CUDA(ctx, cudaMemsetAsync(giant_flag, 0, 4, st));
     B2_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * pl.NB, st));
     uint32_t sblocks = (uint32_t)ctx->sm_count * 8;
     if (n) {
@@ -634,7 +641,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
         {
             ProfScope ps_(ctx, PROF_MSM_ACCUM);
-            msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads);
+            msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads, giant_flag);
         }
         B2_LAUNCH_CHECK(ctx);
         {
@@ -646,13 +653,13 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             XYZZ *in_val = pval, *out_val = pval2;
             while (nrec > 2048) {
                 uint64_t nt = (nrec + COMBINE_LR - 1) / COMBINE_LR;
-                msm_combine_level<<<(uint32_t)((nt + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets, out_id, out_val, nt);
+                msm_combine_level<<<(uint32_t)((nt + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets, out_id, out_val, nt, giant_flag);
                 B2_LAUNCH_CHECK(ctx);
                 nrec = 2 * nt;
                 uint32_t* ti = in_id; in_id = out_id; out_id = ti;
                 XYZZ* tv = in_val; in_val = out_val; out_val = tv;
             }
-            msm_combine_final<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets);
+            msm_combine_final<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets, giant_flag);
             B2_LAUNCH_CHECK(ctx);
         }
     }
