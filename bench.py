@@ -39,7 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_WITNESS_COLS, N_UNIFORM_COLS, N_COEFF_MSMS = 19, 9, 7
-METRIC = "chunk-proof wall-sec (degree-24 layer poly-arith replay)"
+def metric_name(k: int) -> str:
+    return f"chunk-proof wall-sec (degree-{k} layer poly-arith replay)"
 # measured on this pool's B200 (profiles/microbench_r01.jsonl): sustained Montgomery products/s and the
 # INT32 multiply-pipe rate they imply; nominal = 148 SM x 32 IMAD.WIDE lanes/clk x 1.965 GHz
 IMAD_PEAK_MEASURED_GMAC32 = 8500.0
@@ -123,34 +124,46 @@ class ClockSampler:
 # ====================================================================================================
 # reference arm / cpu_baseline: the oracle's restatement of halo2_proofs' Rayon path on the host cores
 # ====================================================================================================
-def cpu_sample(k: int, threads: int, seed: int = 1):
+_CPU_INPUTS = {}
+
+
+def _cpu_inputs(k: int, threads: int):
+    """bases / scalars / domain for the CPU legs, generated once per size (not part of any timed region)."""
+    from oracle import oracle as O  # ORACLE: allowed here only (cpu_baseline / --impl reference)
+
+    if k not in _CPU_INPUTS:
+        n = 1 << k
+        _CPU_INPUTS[k] = (O.fill_points_chain(n, 7, threads), O.fill_fr(n, 1, True), O.fill_fr(n, 2, False), O.EvaluationDomain(5, k))
+    return _CPU_INPUTS[k]
+
+
+def cpu_sample(k: int, threads: int, calibrate: bool = True):
     """Times a bounded sample of the step on the CPU: 1 witness-like MSM, 1 uniform MSM, 1 iNTT 2^k,
     1 coset NTT 2^(k+2); the step is extrapolated by op counts.  Returns (step_seconds, detail)."""
     from oracle import oracle as O  # ORACLE: allowed here only (cpu_baseline / --impl reference)
 
     n = 1 << k
-    bases = O.fill_points_chain(n, 7, threads)
-    sw, su = O.fill_fr(n, seed, True), O.fill_fr(n, seed + 1, False)
-    dom = O.EvaluationDomain(5, k)
+    bases, sw, su, dom = _cpu_inputs(k, threads)
     t = {}
     t0 = time.perf_counter(); O.best_multiexp(sw, bases, threads); t["msm_w"] = time.perf_counter() - t0
     t0 = time.perf_counter(); O.best_multiexp(su, bases, threads); t["msm_u"] = time.perf_counter() - t0
     t0 = time.perf_counter(); coeff = dom.lagrange_to_coeff(su, threads); t["intt"] = time.perf_counter() - t0
     t0 = time.perf_counter(); dom.coeff_to_extended(coeff, threads); t["coset"] = time.perf_counter() - t0
-    # how many of the nominal host threads actually run in parallel (containers are often CPU-quota limited):
-    # one 2^13-point chunk alone vs one such chunk per thread, all at once
-    m = min(1 << 14, n)
-    reps = np.tile(su[:m], (threads, 1)); rb = np.tile(bases[:m], (threads, 1))
-    t1 = tT = 1e30
-    for _ in range(2):
-        t0 = time.perf_counter(); O.best_multiexp(su[:m], bases[:m], 1); t1 = min(t1, time.perf_counter() - t0)
-        t0 = time.perf_counter(); O.best_multiexp(reps, rb, threads); tT = min(tT, time.perf_counter() - t0)
-    t["effective_parallelism"] = round(threads * t1 / tT, 1) if tT > 0 else None
-    t["affinity"] = len(os.sched_getaffinity(0))
-    for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
-        if os.path.exists(f):
-            t["cgroup_cpu"] = open(f).read().strip()
-            break
+    if calibrate:
+        # how many of the nominal host threads actually run in parallel (containers are often CPU-quota limited):
+        # one 2^14-point chunk alone vs one such chunk per thread, all at once
+        m = min(1 << 14, n)
+        reps = np.tile(su[:m], (threads, 1)); rb = np.tile(bases[:m], (threads, 1))
+        t1 = tT = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter(); O.best_multiexp(su[:m], bases[:m], 1); t1 = min(t1, time.perf_counter() - t0)
+            t0 = time.perf_counter(); O.best_multiexp(reps, rb, threads); tT = min(tT, time.perf_counter() - t0)
+        t["effective_parallelism"] = round(threads * t1 / tT, 1) if tT > 0 else None
+        t["affinity"] = len(os.sched_getaffinity(0))
+        for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+            if os.path.exists(f):
+                t["cgroup_cpu"] = open(f).read().strip()
+                break
     step = (N_WITNESS_COLS * t["msm_w"] + (N_UNIFORM_COLS + N_COEFF_MSMS) * t["msm_u"]
             + (N_WITNESS_COLS + N_UNIFORM_COLS) * (t["intt"] + t["coset"]) + t["coset"])
     return step, t
@@ -161,17 +174,35 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    vals = []
+    _cpu_inputs(args.k, threads)
+    vals, detail, budget_s, t_start, reduced = [], None, 240.0, time.perf_counter(), 0
+    scale = None
     for i in range(args.warmup + args.steps):
-        step, detail = cpu_sample(args.k, threads, seed=1 + i)
+        elapsed = time.perf_counter() - t_start
+        left = args.warmup + args.steps - i
+        if scale is not None and vals_full and elapsed + left * vals_full[-1][1] > budget_s and args.k >= 16:
+            # keep the whole run within a few minutes: the remaining iterations time the same ops two sizes down and
+            # are scaled by the full/small ratio measured on this box
+            st, _ = cpu_sample(args.k - 2, threads, calibrate=False)
+            step, reduced = st * scale, reduced + 1
+        else:
+            t0 = time.perf_counter()
+            step, detail = cpu_sample(args.k, threads, calibrate=(i == 0))
+            if i == 0:
+                vals_full = []
+                small, _ = cpu_sample(args.k - 2, threads, calibrate=False) if args.k >= 16 else (None, None)
+                scale = (step / small) if small else None
+            vals_full.append((step, time.perf_counter() - t0))
         if i >= args.warmup:
             vals.append(step)
     v = sum(vals) / len(vals)
-    sample = "per step: 1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d timed on all host threads; " \
-             "step extrapolated by op counts (19/16 MSM, 28 iNTT, 29 coset NTT)" % (args.k, args.k, args.k + 2)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+    sample = ("per step: 1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d timed on %d host threads; step "
+              "extrapolated by op counts (19/16 MSM, 28 iNTT, 29 coset NTT); %d of %d iterations ran the same ops at 2^%d "
+              "scaled by the measured full/small ratio to bound the run" % (args.k, args.k, args.k + 2, threads, reduced,
+                                                                              args.warmup + args.steps, args.k - 2))
+    line = {"impl": "reference", "metric": metric_name(args.k), "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32x8 (254-bit Montgomery, u64x4 on CPU)", "data": "synthetic", "config": {"workload": workload_desc(args.k)},
+            "dtype": "u64x4 (254-bit Montgomery integers on the CPU)", "data": "synthetic", "config": {"workload": workload_desc(args.k), "k": args.k},
             "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample, "detail_s": detail},
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -392,7 +423,7 @@ def run_b200(args):
                    "sample": "1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d on all host threads; step "
                              "extrapolated by op counts" % (k, k, ek), "detail_s": detail}
         line = {
-            "metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args.k), "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
             "config": {"workload": workload_desc(k), "k": k, "msm_window_bits": c_bits, "msm_windows": W,

@@ -238,15 +238,9 @@ ntt_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __res
             st_sm(lo, hi, i1, b1 + d1);
             st_sm(lo, hi, i3, b1 - d1);
         }
-        // The q -> (lane, group) mapping keeps the data of stages 1-4 inside one warp (a warp owns 16 digit positions x
-        // 8 lanes, or 128 positions when C = 1) and of stages 5-6 inside a 128-thread group (64 positions), so the
-        // first barrier is a __syncwarp and the second a 128-thread named barrier; only later stages need the block.
-        if (s == 1 && m >= 3)
-            __syncwarp();
-        else if (s == 3 && m >= 5 && C == 8 && NT == 256)
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + (tid >> 7)), "r"(128) : "memory");
-        else
-            __syncthreads();
+        // (measured: replacing this barrier by __syncwarp / 128-thread named barriers for the warp-local early stages
+        //  gave -1 % at 2^24 and +5 % at 2^26, so the plain block barrier stays)
+        __syncthreads();
     }
     if (s == m) {
         const uint32_t half = 1u << (s - 1);
