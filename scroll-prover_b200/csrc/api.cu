@@ -257,7 +257,10 @@ int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalar
         return fail(ctx, B200ZK_E_INVALID, "msm_g1: %llu scalars but only %llu bases (assert_eq!(coeffs.len(), bases.len()))",
                     (unsigned long long)n, (unsigned long long)srs->n);
     Guard g(ctx);
-    return msm_common(ctx, (const Affine*)srs->dev_bases, scalars, n, out_jacobian96, srs->pre_c, srs->n);
+    // a commit over a short prefix of a large precomputed SRS is cheaper with the plain bases (table 0) and a window
+    // sized for n than with the handle's wide window (2^(c-1) buckets to reduce)
+    uint32_t pre_c = (srs->pre_c && n * 16 >= srs->n) ? srs->pre_c : 0;
+    return msm_common(ctx, (const Affine*)srs->dev_bases, scalars, n, out_jacobian96, pre_c, srs->n);
 }
 
 int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96) {
@@ -432,7 +435,8 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
         if (j + 1 < count) B2_TRY(upload(j + 1));
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
         const Fr* col = (const Fr*)ctx->colstage[b].p;
-        if (do_commit) B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, srs->pre_c, srs->n));
+        if (do_commit)
+            B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, (n * 16 >= srs->n) ? srs->pre_c : 0, srs->n));
         if (mode >= 1) {
             Fr* coeff = (coeff_out_dev && coeff_out_dev[j]) ? (Fr*)coeff_out_dev[j] : (Fr*)ctx->col_coeff.p;
             B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
