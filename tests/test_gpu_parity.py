@@ -388,6 +388,30 @@ def test_device_resident_buffers(ctx, zk):
     assert np.array_equal(back.cpu().numpy().view(np.uint64)[: 1 << k], coeff_exp)
 
 
+# --------------------------------------------------------------------------- empty / degenerate inputs
+def test_degenerate_inputs(ctx, zk):
+    one = O.fill_fr(1, 5)
+    x = one.copy()
+    ctx.best_fft(x, O.const_fr("fr_ONE"), 0)  # length-1 transform is the identity
+    assert np.array_equal(x, one)
+    z = np.zeros((64, 4), np.uint64)
+    pts = O.fill_points(64, 3, 4)
+    got = ctx.best_multiexp(z, pts)  # all-zero scalars: every digit skipped
+    assert not got[8:].any() and np.array_equal(got[4:8], O.const_fr("fq_ONE"))  # identity (0, 1, 0)
+    got = ctx.best_multiexp(O.fill_fr(64, 9), np.zeros((64, 8), np.uint64))  # all bases at infinity
+    assert not got[8:].any()
+    assert ctx.poly_add(np.zeros((0, 4), np.uint64), np.zeros((0, 4), np.uint64)).shape == (0, 4)
+    assert not ctx.eval_polynomial(np.zeros((0, 4), np.uint64), one[0]).any()  # empty polynomial evaluates to 0
+    assert ctx.kate_division(one, one[0]).shape == (0, 4)
+    srs = ctx.srs_register(pts)
+    assert zk.commit_columns(ctx, srs, [], 6, mode=0).shape == (0, 12)
+    assert not srs.msm(np.zeros((0, 4), np.uint64), n=0)[8:].any()
+    srs.release()
+    inv = np.zeros((5, 4), np.uint64)
+    ctx.batch_invert(inv)  # zeros stay zero
+    assert not inv.any()
+
+
 # --------------------------------------------------------------------------- BASELINE full sizes (properties)
 def test_full_size_degree24_column(ctx, zk):
     """configs[1] sizes: one 2^24 column through commit_lagrange -> lagrange_to_coeff -> coeff_to_extended (2^26) ->
