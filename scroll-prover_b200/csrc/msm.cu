@@ -27,9 +27,8 @@ static constexpr uint32_t PART_INVALID = 0x1fffffffu;  // also the bucket-id mas
 static constexpr uint32_t PART_GIANT = 0x20000000u;
 static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
-static constexpr int ACC_L = 128;       // sorted entries per accumulate thread
+static constexpr int ACC_L_DEFAULT = 128;  // sorted entries per accumulate thread (B200ZK_ACC_L overrides, experiments)
 static constexpr int GROUP = 32;        // buckets per first-level reduction group
-static constexpr uint32_t BIG_BUCKET = 4 * ACC_L;  // buckets above this size are split over threads
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -220,10 +219,11 @@ __device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
 __global__ void __launch_bounds__(256, 2)
 msm_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                uint64_t NB, XYZZ* __restrict__ buckets, uint32_t* __restrict__ part_id, XYZZ* __restrict__ part_val,
-               uint64_t nthreads, uint32_t* __restrict__ giant_flag) {
+               uint64_t nthreads, uint32_t* __restrict__ giant_flag, uint32_t ACC_L) {
     uint64_t tau = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tau >= nthreads) return;
     const uint32_t M = offsets[NB];
+    const uint32_t BIG_BUCKET = 4 * ACC_L;  // buckets above this size are split over threads
     uint64_t start = tau * ACC_L;
     part_id[2 * tau] = PART_INVALID;
     part_id[2 * tau + 1] = PART_INVALID;
@@ -557,6 +557,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     ctx->last_windows = pl.W;
     ctx->last_adds = max_entries;
 
+    const uint32_t ACC_L = ctx->msm_acc_l ? ctx->msm_acc_l : (uint32_t)ACC_L_DEFAULT;
     uint64_t nthreads = (max_entries + ACC_L - 1) / ACC_L;
     if (nthreads == 0) nthreads = 1;
     uint32_t ntiles = (uint32_t)((pl.NB + SCAN_TILE - 1) / SCAN_TILE);
@@ -641,7 +642,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
         {
             ProfScope ps_(ctx, PROF_MSM_ACCUM);
-            msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads, giant_flag);
+            msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads, giant_flag, ACC_L);
         }
         B2_LAUNCH_CHECK(ctx);
         {
