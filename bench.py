@@ -301,10 +301,10 @@ def run_b200(args):
     host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
             "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
     hstage = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev) if host["h"] is not None else None
-    if world == 1:  # every column crosses PCIe once (commitment + transforms in one mode-2 call)
-        h2d_bytes = (N_WITNESS_COLS + N_UNIFORM_COLS + N_COEFF_MSMS) * n * 32 + (1 << ek) * 32
-    else:
-        h2d_bytes = sum((1 << ek) * 32 if j[0] == "icoset" else n * 32 for j in my_jobs)
+    # a column whose commitment and transforms are on the same rank crosses PCIe once (one mode-2 call)
+    _nl, _nn = sum(1 for j in my_jobs if j[0] == "lmsm"), sum(1 for j in my_jobs if j[0] == "ntt")
+    h2d_bytes = (max(_nl, _nn) + sum(1 for j in my_jobs if j[0] == "msm")) * n * 32 + \
+        sum((1 << ek) * 32 for j in my_jobs if j[0] == "icoset")
     d2h_bytes = n_msm * 96
 
     lmsm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "lmsm"]
@@ -316,7 +316,7 @@ def run_b200(args):
         """Everything through the C ABI with HOST (pinned) buffers: b200zk_commit_columns double-buffers the H2D of
         column j+1 on its copy stream against the kernels of column j; commitments are read back (D2H) per call."""
         # a column whose commitment and transforms both landed on this rank is uploaded once (mode 2)
-        both = min(len(lmsm_jobs), len(ntt_jobs)) if world == 1 else 0
+        both = min(len(lmsm_jobs), len(ntt_jobs))
         if both:
             zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in lmsm_jobs[:both]], k, mode=2,
                               omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)

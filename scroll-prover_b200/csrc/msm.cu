@@ -7,17 +7,19 @@
 // sum_i s_i * P_i, returned normalised, so its bytes equal the reference's `to_affine()` output.
 //
 // Pipeline (DESIGN.md "MSM"); all of it on the context stream, no host synchronisation inside:
-//   1 msm_count     scalar -> canonical (one Montgomery product), signed c-bit digits, per-bucket histogram
-//   2 scan          exclusive prefix sum of the W * 2^(c-1) bucket counts
-//   3 msm_scatter   counting-sort of (point index | sign) into bucket order
-//   4 msm_accumulate  load-balanced segmented reduction: every thread owns L consecutive sorted entries and
-//                   adds affine bases into an XYZZ accumulator (8M+2S per add); buckets wholly inside a
-//                   chunk are stored directly, chunk-straddling runs go to a partial list
-//   5 msm_combine   partial runs of the same bucket are summed
-//   6 bucket_reduce per-window sum_b b * B_b: groups of 32 buckets by running sums, then a log-depth
-//                   tree with power-of-two doublings
-//   7 msm_finish    Horner over windows, normalisation to (x, y, 1)
-// Zero digits are skipped (witness columns are mostly zeros / small values).
+//   1 msm_count       scalar -> canonical (one Montgomery product), signed c-bit digits -> digits[w*n+i], histogram
+//   2 scan            exclusive prefix sum of the bucket counts (three kernels)
+//   3 msm_scatter     counting sort of (table index | sign) into bucket order; window-major / a few bucket-range
+//                     sweeps so that the random 4-byte stores stay L2-resident
+//   4 msm_accumulate  lock-step segmented reduction: every thread owns L consecutive sorted entries and adds affine
+//                     bases into an XYZZ accumulator (8M+2S per add); buckets wholly inside a chunk are stored
+//                     directly, the <= 2 cut runs become partial records
+//   5 msm_combine_*   partial records: ordinary buckets by their head record, GIANT buckets (> 4L entries: millions
+//                     of equal digits in real witness columns) by a log-depth level reduction
+//   6 msm_rowcol_sums + msm_weighted_sums   sum_b b*B_b per bucket set with a short critical path
+//   7 msm_finish      Horner over bucket sets, normalisation to (x, y, 1)
+// With a precomputed SRS (tables 2^(c*w) P_i, built at registration) all windows share ONE bucket set.
+// Zero scalars and zero digits are skipped (witness columns are mostly zeros / small values).
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -28,14 +30,12 @@ static constexpr uint32_t PART_GIANT = 0x20000000u;
 static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
 static constexpr int ACC_L_DEFAULT = 128;  // sorted entries per accumulate thread (B200ZK_ACC_L overrides, experiments)
-static constexpr int GROUP = 32;        // buckets per first-level reduction group
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
     uint32_t Ws;        // bucket sets: W, or 1 when the SRS holds precomputed 2^(c*w) multiples of every base
     uint64_t stride;    // precomputed SRS: table w starts at bases + w*stride (0 otherwise)
     uint64_t NB;        // Ws * B
-    uint32_t g, G;      // reduction group size, groups per bucket set
 };
 
 __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
@@ -549,8 +549,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     pl.Ws = pre_c ? 1 : pl.W;
     pl.stride = pre_c ? pre_stride : 0;
     pl.NB = (uint64_t)pl.Ws * pl.B;
-    pl.g = pl.B < (uint32_t)GROUP ? pl.B : (uint32_t)GROUP;
-    pl.G = pl.B / pl.g;
     uint64_t max_entries = n * pl.W;
     if (max_entries >= 0xffffffffull) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n*W too large for window %u", pl.c);
     ctx->last_c = pl.c;
