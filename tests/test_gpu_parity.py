@@ -39,6 +39,9 @@ def test_field_ops_match_oracle(ctx, field):
     got_mul = ctx.debug_field_op(field, 0, a, b)
     got_add = ctx.debug_field_op(field, 1, a, b)
     got_sub = ctx.debug_field_op(field, 2, a, b)
+    got_sqr = ctx.debug_field_op(field, 5, a, b)  # dedicated Montgomery squaring
+    for i in list(range(len(edge))) + list(range(0, n, 7)):
+        assert np.array_equal(got_sqr[i], mul(a[i], a[i]))
     for i in range(0, n, 7):
         assert np.array_equal(got_mul[i], mul(a[i], b[i]))
         assert np.array_equal(got_add[i], add(a[i], b[i]))
