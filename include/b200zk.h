@@ -140,6 +140,8 @@ B200ZK_API int32_t b200zk_poly_scale(b200zk_ctx* ctx, void* r, const void* a, co
 B200ZK_API int32_t b200zk_poly_axpy(b200zk_ctx* ctx, void* r, const void* a, const void* s32, const void* b, uint64_t n); /* r = s*a + b */
 /* arithmetic::eval_polynomial(poly, point) */
 B200ZK_API int32_t b200zk_eval_poly(b200zk_ctx* ctx, const void* poly, uint64_t n, const void* point32, void* out32);
+/* arithmetic::compute_inner_product(a, b) = sum_i a_i * b_i */
+B200ZK_API int32_t b200zk_inner_product(b200zk_ctx* ctx, const void* a, const void* b, uint64_t n, void* out32);
 /* ff::BatchInvert on a slice: zeros stay zero */
 B200ZK_API int32_t b200zk_batch_invert(b200zk_ctx* ctx, void* data, uint64_t n);
 /* arithmetic::kate_division: q (n-1 coeffs) = a (n coeffs) / (X - b) */

@@ -86,6 +86,7 @@ def _load():
         "b200zk_poly_scale": [vp, vp, vp, vp, u64],
         "b200zk_poly_axpy": [vp, vp, vp, vp, vp, u64],
         "b200zk_eval_poly": [vp, vp, u64, vp, vp],
+        "b200zk_inner_product": [vp, vp, vp, u64, vp],
         "b200zk_batch_invert": [vp, vp, u64],
         "b200zk_kate_division": [vp, vp, vp, u64, vp],
         "b200zk_debug_field_op": [vp, C.c_int, C.c_int, vp, vp, vp, u64],
@@ -110,7 +111,7 @@ ABI_SYMBOLS = [
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
-    "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_batch_invert",
+    "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
@@ -334,6 +335,15 @@ class Context:
         pp, k1 = _ptr(poly)
         px, k2 = _ptr(point)
         self._ck(lib().b200zk_eval_poly(self._h, pp, n, px, out.ctypes.data))
+        return out
+
+    def compute_inner_product(self, a, b) -> np.ndarray:
+        n = _count(a, 32)
+        assert n == _count(b, 32)
+        out = np.zeros(4, np.uint64)
+        pa, k1 = _ptr(a)
+        pb, k2 = _ptr(b)
+        self._ck(lib().b200zk_inner_product(self._h, pa, pb, n, out.ctypes.data))
         return out
 
     def batch_invert(self, data):

@@ -17,6 +17,7 @@ int32_t g1_generator_mul_run(b200zk_ctx* ctx, const Fr* scalars, uint64_t n, Aff
 int32_t poly_ew(b200zk_ctx* ctx, int op, Fr* r, const Fr* a, const Fr* b, const Fr& s, uint64_t n);
 int32_t eval_poly(b200zk_ctx* ctx, const Fr* poly, uint64_t n, const Fr& x, Fr* out_dev);
 int32_t batch_invert(b200zk_ctx* ctx, Fr* data, uint64_t n);
+int32_t inner_product(b200zk_ctx* ctx, const Fr* a, const Fr* b, uint64_t n, Fr* out_dev);
 int32_t kate_division(b200zk_ctx* ctx, Fr* q, const Fr* a, uint64_t n, const Fr& b);
 int32_t g1_fft_run(b200zk_ctx* ctx, const void* in, bool from_jac, void* out, bool to_jac, uint32_t log_n, const Fr& omega,
                    const Fr* scale);
@@ -498,6 +499,23 @@ int32_t b200zk_eval_poly(b200zk_ctx* ctx, const void* poly, uint64_t n, const vo
         const void* p_dev = nullptr;
         B2_TRY(stage_in(ctx, ctx->stage_in, poly, sizeof(Fr) * n, &p_dev));
         B2_TRY(eval_poly(ctx, (const Fr*)p_dev, n, x, res));
+    }
+    return deliver(ctx, out32, res, sizeof(Fr));
+}
+
+int32_t b200zk_inner_product(b200zk_ctx* ctx, const void* a, const void* b, uint64_t n, void* out32) {
+    CHECK_CTX(ctx);
+    if (!out32 || (n && (!a || !b))) return fail(ctx, B200ZK_E_INVALID, "inner_product: null pointer");
+    Guard g(ctx);
+    B2_TRY(scratch_reserve(ctx, ctx->stage_out, 256));
+    Fr* res = (Fr*)ctx->stage_out.p;
+    if (!n) {
+        B2_CUDA(ctx, cudaMemsetAsync(res, 0, sizeof(Fr), ctx->stream));
+    } else {
+        const void *a_dev = nullptr, *b_dev = nullptr;
+        B2_TRY(stage_in(ctx, ctx->stage_in, a, sizeof(Fr) * n, &a_dev));
+        B2_TRY(stage_in(ctx, ctx->ntt_work, b, sizeof(Fr) * n, &b_dev));
+        B2_TRY(inner_product(ctx, (const Fr*)a_dev, (const Fr*)b_dev, n, res));
     }
     return deliver(ctx, out32, res, sizeof(Fr));
 }

@@ -108,6 +108,27 @@ int32_t eval_poly(b200zk_ctx* ctx, const Fr* poly, uint64_t n, const Fr& x, Fr* 
     return B200ZK_OK;
 }
 
+// ---- compute_inner_product(a, b) = sum_i a_i b_i
+__global__ void __launch_bounds__(256) inner_product_kernel(const Fr* a, const Fr* b, uint64_t n, Fr* partial) {
+    __shared__ Fr sh[256];
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    Fr acc = Fr::zero();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc = acc + pl_ld(a + i) * pl_ld(b + i);
+    Fr s = block_sum(acc, sh);
+    if (threadIdx.x == 0) pl_st(partial + blockIdx.x, s);
+}
+
+int32_t inner_product(b200zk_ctx* ctx, const Fr* a, const Fr* b, uint64_t n, Fr* out_dev) {
+    uint32_t blocks = ew_blocks(ctx, n);
+    B2_TRY(scratch_reserve(ctx, ctx->misc, sizeof(Fr) * (blocks + 1)));
+    Fr* partial = (Fr*)ctx->misc.p;
+    inner_product_kernel<<<blocks, 256, 0, ctx->stream>>>(a, b, n, partial);
+    B2_LAUNCH_CHECK(ctx);
+    sum_fr_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, out_dev);
+    B2_LAUNCH_CHECK(ctx);
+    return B200ZK_OK;
+}
+
 // ---- batch inversion (Montgomery's trick per thread over a strided slice; zeros stay zero)
 __global__ void __launch_bounds__(256) batch_invert_kernel(Fr* data, Fr* prefix, uint64_t n, uint32_t T) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -257,6 +257,23 @@ class ParamsKZG {
     // Params::commit_lagrange(poly, Blind)
     G1 commit_lagrange(const std::vector<Fr>& poly) { return msm(dev_gl_, g_lagrange, B200ZK_SRS_G_LAGRANGE, poly); }
 
+    // Params::downsize(k): truncate g and rebuild g_lagrange with the G1 FFT on the device
+    // (reference call site /root/reference/integration/tests/integration.rs:17-18)
+    void downsize(uint32_t new_k) {
+        if (new_k > k) throw Panic("assertion failed: k <= self.k");
+        release();
+        k = new_k;
+        n = 1ull << new_k;
+        g.resize(n);
+        g_lagrange.resize(n);
+        auto& b = Backend::get();
+        b.check(b200zk_g_to_lagrange(b.ctx(), g.data(), new_k, g_lagrange.data()), "downsize");
+    }
+
+    // device handles (registered lazily): for b200zk_commit_columns and other batched entry points
+    b200zk_srs* lagrange_handle() { return handle(dev_gl_, g_lagrange, B200ZK_SRS_G_LAGRANGE); }
+    b200zk_srs* monomial_handle() { return handle(dev_g_, g, B200ZK_SRS_G); }
+
     void release() {
         auto* c = Backend::get().ctx();
         if (dev_g_) b200zk_srs_release(c, dev_g_);
@@ -266,14 +283,33 @@ class ParamsKZG {
 
   private:
     b200zk_srs *dev_g_ = nullptr, *dev_gl_ = nullptr;
+    b200zk_srs* handle(b200zk_srs*& h, const std::vector<G1Affine>& bases, uint32_t tag) {
+        auto& b = Backend::get();
+        if (!h) b.check(b200zk_srs_register(b.ctx(), bases.data(), bases.size(), tag, &h), "srs_register");  // once, lazily
+        return h;
+    }
     G1 msm(b200zk_srs*& h, const std::vector<G1Affine>& bases, uint32_t tag, const std::vector<Fr>& poly) {
         if (poly.size() > bases.size()) throw Panic("assertion failed: `(left == right)` coeffs.len() == bases.len()");
         auto& b = Backend::get();
-        if (!h) b.check(b200zk_srs_register(b.ctx(), bases.data(), bases.size(), tag, &h), "srs_register");  // once, lazily
+        handle(h, bases, tag);
         G1 out;
         b.check(b200zk_msm_g1(b.ctx(), h, poly.data(), poly.size(), &out), "commit");
         return out;
     }
 };
+
+// The per-column work of one create_proof phase for a batch of Lagrange-form columns held on the host:
+// commitments[j] = commit_lagrange(cols[j]); with mode >= 1 the coefficient form (and with mode 2 the extended coset
+// evaluations) are produced on the device into coeff_dev[j] / ext_dev[j] (b200zk_buf_alloc handles; may be null).
+inline std::vector<G1> commit_columns(ParamsKZG& params, const EvaluationDomain& dom, const std::vector<const Fr*>& cols, int mode,
+                                      void* const* coeff_dev = nullptr, void* const* ext_dev = nullptr) {
+    std::vector<G1> out(cols.size());
+    auto& b = Backend::get();
+    std::vector<const void*> ptrs(cols.begin(), cols.end());
+    b.check(b200zk_commit_columns(b.ctx(), params.lagrange_handle(), ptrs.data(), (uint32_t)ptrs.size(), dom.k, &dom.omega_inv,
+                                  &dom.extended_omega, dom.extended_k, out.data(), coeff_dev, ext_dev, mode),
+            "commit_columns");
+    return out;
+}
 
 }  // namespace halo2_b200

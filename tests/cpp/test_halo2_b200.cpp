@@ -103,6 +103,24 @@ int main() {
     for (size_t i = 0; i < n; ++i) REQUIRE(coeffs4[i] == poly[i]);
     for (size_t i = n; i < 4 * n; ++i) REQUIRE((coeffs4[i].l[0] | coeffs4[i].l[1] | coeffs4[i].l[2] | coeffs4[i].l[3]) == 0);
 
+    // batched column pipeline: commitments equal commit_lagrange; device coefficient form equals lagrange_to_coeff
+    {
+        std::vector<Fr> col2(n);
+        for (auto& c : col2) c = rand_fr();
+        void* coeff_dev[2] = {nullptr, nullptr};
+        REQUIRE(b200zk_buf_alloc(Backend::get().ctx(), 32 * n, &coeff_dev[0]) == B200ZK_OK);
+        REQUIRE(b200zk_buf_alloc(Backend::get().ctx(), 32 * n, &coeff_dev[1]) == B200ZK_OK);
+        std::vector<const Fr*> cols = {evals.data(), col2.data()};
+        std::vector<G1> cm = commit_columns(params, dom, cols, 1, coeff_dev, nullptr);
+        G1 e0 = params.commit_lagrange(evals), e1 = params.commit_lagrange(col2);
+        REQUIRE(std::memcmp(&cm[0], &e0, 96) == 0 && std::memcmp(&cm[1], &e1, 96) == 0);
+        std::vector<Fr> got(n);
+        REQUIRE(b200zk_buf_download(Backend::get().ctx(), got.data(), coeff_dev[0], 32 * n) == B200ZK_OK);
+        REQUIRE(got == poly);  // evals = NTT(poly)
+        b200zk_buf_free(Backend::get().ctx(), coeff_dev[0]);
+        b200zk_buf_free(Backend::get().ctx(), coeff_dev[1]);
+    }
+
     // best_multiexp: generic bases, shorter slices, and the reference's length assertion
     std::vector<Fr> sc(poly.begin(), poly.begin() + 100);
     std::vector<G1Affine> bs(params.g.begin(), params.g.begin() + 100);
@@ -143,6 +161,18 @@ int main() {
     G1 c3 = p2.commit(poly);
     REQUIRE(std::memcmp(&c1, &c3, 96) == 0);
     std::remove(path);
+
+    // Params::downsize: g_lagrange of the smaller domain is rebuilt by the device G1 FFT; commit == commit_lagrange again
+    p2.downsize(k - 2);
+    {
+        EvaluationDomain d2 = EvaluationDomain::new_(5, k - 2);
+        std::vector<Fr> small(poly.begin(), poly.begin() + (n >> 2));
+        G1 a1 = p2.commit(small);
+        std::vector<Fr> ev = small;
+        arithmetic::best_fft(ev, d2.omega, k - 2);
+        G1 a2 = p2.commit_lagrange(ev);
+        REQUIRE(std::memcmp(&a1, &a2, 96) == 0);
+    }
 
     std::printf("ALL OK\n");
     return 0;

@@ -3,6 +3,7 @@ include/b200zk.h declares, and the product refuses to run without a GPU (no CPU 
 import ctypes
 import os
 import re
+import shutil
 import subprocess
 import sys
 
@@ -16,7 +17,8 @@ HEADER = os.path.join(ROOT, "include", "b200zk.h")
 def built_lib():
     sys.path.insert(0, os.path.join(ROOT, "scroll-prover_b200"))
     lib_path = os.path.join(ROOT, "scroll-prover_b200", "libb200zk.so")
-    if not os.path.exists(lib_path):
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+        # incremental: a no-op when the .so is newer than every source, a rebuild when a kernel was edited
         subprocess.check_call([sys.executable, os.path.join(ROOT, "scroll-prover_b200", "build.py")])
     return lib_path
 

@@ -108,6 +108,23 @@ def test_evaluation_domain_matches_oracle(ctx, zk, k):
     assert np.array_equal(back[: 1 << k], coeff_exp) and not back[1 << k:].any()
 
 
+@pytest.mark.parametrize("log_in,log_n", [(0, 3), (5, 6), (6, 9), (9, 12), (10, 13), (13, 13), (14, 17)])
+def test_zero_padded_transform_any_extension(ctx, log_in, log_n):
+    """b200zk_ntt_fr_ext with log_in < log_n (domains whose quotient degree gives extended_k - k = 1, 3, ...): equals
+    best_fft of the explicitly zero-padded vector, with and without the zeta coset pre-scaling."""
+    a = O.fill_fr(1 << log_in, SEED + 50 + log_n)
+    w = omega_for(log_n)
+    padded = np.zeros((1 << log_n, 4), np.uint64)
+    padded[: 1 << log_in] = a
+    out = np.zeros((1 << log_n, 4), np.uint64)
+    ctx.ntt_ext(a, log_in, out, log_n, w)
+    assert np.array_equal(out, O.best_fft(padded, w, log_n, threads=4))
+    dom_like = O.EvaluationDomain(5, 3)  # only for distribute_powers_zeta
+    pre = dom_like.distribute_powers_zeta(padded, True)
+    ctx.ntt_ext(a, log_in, out, log_n, w, False, 1)
+    assert np.array_equal(out, O.best_fft(pre, w, log_n, threads=4))
+
+
 @pytest.mark.parametrize("log_n", [20, 22])
 def test_large_fft_properties(ctx, log_n):
     """BASELINE config 1 size (2^20) and beyond: linearity + round trip + spot check against naive evaluation."""
@@ -337,6 +354,7 @@ def test_poly_ops_match_oracle(ctx, n):
     x = O.fill_fr(1, SEED + 603)[0]
     assert np.array_equal(ctx.eval_polynomial(a, x), O.eval_polynomial(a, x))
     assert np.array_equal(ctx.kate_division(a, x), O.kate_division(a, x))
+    assert np.array_equal(ctx.compute_inner_product(a, b), O.compute_inner_product(a, b))
     inv = b.copy()
     ctx.batch_invert(inv)
     assert np.array_equal(inv, O.fr_batch_invert(b))
