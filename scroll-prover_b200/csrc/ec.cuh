@@ -86,12 +86,10 @@ FF_HD void xyzz_madd(XYZZ& acc, const Fq& qx, const Fq& qy) {
             acc = XYZZ::identity();
         return;
     }
-    // general products for the two squarings: measured on B200, the dedicated sqr() (100 IMAD.WIDE but a serial
-    // product-scanning chain) makes msm_accumulate 2 % SLOWER than the 128-MAC product with its two parallel chains
-    Fq PP = P * P;
+    Fq PP = P.sqr();
     Fq PPP = P * PP;
     Fq Q = acc.x * PP;
-    Fq X3 = R * R - PPP - Q.dbl();
+    Fq X3 = R.sqr() - PPP - Q.dbl();
     Fq Y3 = R * (Q - X3) - acc.y * PPP;
     acc.x = X3;
     acc.y = Y3;

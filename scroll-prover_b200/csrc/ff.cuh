@@ -393,10 +393,16 @@ struct Fp {
         final_sub(r.l.v);
         return r;
     }
-    // Montgomery square: 36 product MACs (28 off-diagonal by product scanning, doubled, + 8 diagonal) followed by the
-    // 64 reduction MACs -- 100 IMAD.WIDE instead of the 128 of a general product.  The carries that leave a reduction
-    // row land at limb >= 8 and never influence a later Montgomery quotient, so they are collected and added once.
-    FF_HD Fp sqr() const {
+    // sqr(): the general product.  Measured on B200 (profiles/, round 1): the dedicated square below issues 100
+    // instead of 128 IMAD.WIDE but its product-scanning column chain is serial, so msm_accumulate got 2 % slower and the
+    // latency-bound bucket-reduction kernels do not want a longer dependency chain either.
+    FF_HD Fp sqr() const { return (*this) * (*this); }
+
+    // Dedicated Montgomery square (kept, tested, for throughput-bound tooling such as the fixed-base generator
+    // multiplication): 36 product MACs (28 off-diagonal by product scanning, doubled, + 8 diagonal) followed by the 64
+    // reduction MACs.  The carries that leave a reduction row land at limb >= 8 and never influence a later
+    // Montgomery quotient, so they are collected and added once.
+    FF_HD Fp sqr_scan() const {
         const uint32_t* a = l.v;
         uint32_t off[16], d[16], t[17];
         uint32_t c0 = 0, c1 = 0, c2 = 0;

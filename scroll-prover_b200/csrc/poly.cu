@@ -231,7 +231,7 @@ __global__ void field_op_kernel(int op, F* r, const F* a, const F* b, uint64_t n
         case 2: o = x - y; break;
         case 3: o = x.inv(); break;
         case 4: o = x.from_mont(); break;
-        default: o = x.sqr(); break;
+        default: o = x.sqr_scan(); break;
     }
     r[i] = o;
 }

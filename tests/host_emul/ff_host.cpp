@@ -16,7 +16,7 @@ template <class F> static void binop(int op, uint32_t* r, const uint32_t* a, con
         case 4: z = x.from_mont(); break;
         case 5: z = x.to_mont(); break;
         case 6: z = x.neg(); break;
-        default: z = x.sqr(); break;
+        default: z = x.sqr_scan(); break;
     }
     memcpy(r, z.l.v, 32);
 }
