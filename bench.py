@@ -315,21 +315,18 @@ def run_b200(args):
     def step_e2e():
         """Everything through the C ABI with HOST (pinned) buffers: b200zk_commit_columns double-buffers the H2D of
         column j+1 on its copy stream against the kernels of column j; commitments are read back (D2H) per call."""
-        # a column whose commitment and transforms both landed on this rank is uploaded once (mode 2)
+        # ONE b200zk_run_column_jobs call for everything this rank owns: a column whose commitment and transforms both
+        # landed here is uploaded once (mode 2); the quotient's extended_to_coeff is a mode-4 job of the same pipeline
         both = min(len(lmsm_jobs), len(ntt_jobs))
-        if both:
-            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in lmsm_jobs[:both]], k, mode=2,
-                              omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)
-        if lmsm_jobs[both:]:
-            zk.commit_columns(ctx, params._gl, [host[job[1]][j % 2] for j, job in lmsm_jobs[both:]], k, mode=0)
-        if ntt_jobs[both:]:
-            zk.commit_columns(ctx, None, [host[job[1]][j % 2] for j, job in ntt_jobs[both:]], k, mode=3,
-                              omega_inv=dom.omega_inv, extended_omega=dom.extended_omega, extended_k=ek)
-        if msm_jobs:
-            zk.commit_columns(ctx, params._g, [host[job[1]][j % 2] for j, job in msm_jobs], k, mode=0)
+        jl = [(host[job[1]][j % 2], params._gl, 2, None, None) for j, job in lmsm_jobs[:both]]
+        jl += [(host[job[1]][j % 2], params._gl, 0, None, None) for j, job in lmsm_jobs[both:]]
+        jl += [(host[job[1]][j % 2], None, 3, None, None) for j, job in ntt_jobs[both:]]
+        jl += [(host[job[1]][j % 2], params._g, 0, None, None) for j, job in msm_jobs]
         if has_icoset:
-            ctx.buf_upload(hstage, host["h"])
-            ctx.best_fft(hstage, dom.extended_omega_inv, ek, inverse_scale=True, coset_mode=zk.COSET_POST)
+            jl.append((host["h"], None, 4, None, None))
+        if jl:
+            zk.run_column_jobs(ctx, jl, k, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
+                               extended_omega_inv=dom.extended_omega_inv, extended_k=ek)
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -412,6 +409,18 @@ def run_b200(args):
         # algorithmic MAC32 of the accumulate launches = bucket additions actually performed (non-zero signed digits;
         # witness-like columns skip most of the N*W upper bound) x 1280 MAC32 per mixed add
         acc_achieved = (actual_adds * MAC32_PER_MADD) / (acc_ms * 1e-3) / 1e9 if acc_ms else None
+        traffic, traffic_note = None, None
+        try:  # DRAM bytes of one msm_accumulate launch from the committed `ncu --set full` capture (uniform 2^24 MSM)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_v6_summary.json")))
+            for e in ncu["kernels"]:
+                if e["kernel"].startswith("msm_accumulate"):
+                    rd, wr = float(e["dram__bytes_read.sum"].split()[0]), float(e["dram__bytes_write.sum"].split()[0])
+                    traffic = (rd + wr) * 1e9
+                    traffic_note = ("dram__bytes_read+write of ONE msm_accumulate launch (MSM 2^24, uniform scalars, 201 M adds) "
+                                    "from profiles/ncu_r01_v6_summary.json; algorithmic bytes of that launch = 201e6 x 68 B = 13.7e9")
+                    break
+        except Exception:
+            pass
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ntt_gbs = my_ntt_bytes * args.steps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
@@ -437,15 +446,15 @@ def run_b200(args):
                          "peak": IMAD_PEAK_MEASURED_GMAC32, "peak_nominal": IMAD_PEAK_NOMINAL_GMAC32, "unit": "GMAC32/s",
                          "frac": acc_achieved / IMAD_PEAK_MEASURED_GMAC32 if acc_achieved else None,
                          "peak_source": "measured Montgomery-product microbenchmark (profiles/microbench_r01.jsonl), not in MEASURED_PEAKS.json",
-                         "traffic": None,
+                         "traffic": traffic, "traffic_note": traffic_note,
                          "hbm": {"kernel": "ntt_pass", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": ntt_gbs / hbm_peak if ntt_gbs else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "kernel_ms_per_step_rank0": {c: prof[c]["ms"] / args.steps for c in prof if prof[c]["count"]},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "api": "C ABI with pinned HOST buffers: b200zk_commit_columns (mode 2 for the 28 columns, mode 0 for the 7 "
-                           "coefficient commits; H2D double-buffered on the library's copy stream), b200zk_buf_upload + "
-                           "b200zk_ntt_fr for the quotient (rank 0 bytes)"},
+                    "api": "ONE C-ABI call per step with pinned HOST buffers: b200zk_run_column_jobs (mode 2 for the 28 columns, "
+                           "mode 0 for the 7 coefficient commits, mode 4 for the quotient; H2D double-buffered on the library's "
+                           "copy stream; rank 0 bytes)"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_per_step": wall,
         }
         print(json.dumps(line))

@@ -128,6 +128,21 @@ B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t l
  *           multi-GPU caller place a column's MSM and its transforms on different ranks
  * commits_out: count x 96 B normalised Jacobian points (host or device).  No host synchronisation inside the loop;
  * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs. */
+/* Heterogeneous form: every job names its own host buffer, SRS and mode, so one proof phase (Lagrange commits,
+ * coefficient-form commits, transforms, and the quotient's extended_to_coeff) is ONE call with a full copy/compute pipeline:
+ *   mode 0..3 as above (host_values holds 2^k elements);
+ *   mode 4: extended_to_coeff of 2^extended_k host values (inverse coset NTT) into coeff_out_dev or an internal scratch.
+ * commits_out gets count x 96 B; entries of jobs without a commitment are zero. */
+typedef struct b200zk_column_job {
+    const void* host_values;
+    const b200zk_srs* srs;    /* modes 0, 1, 2 */
+    int32_t mode;
+    void* coeff_out_dev;      /* optional device output (2^k elements; 2^extended_k for mode 4) */
+    void* ext_out_dev;        /* optional device output (2^extended_k elements) */
+} b200zk_column_job;
+B200ZK_API int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k,
+                                          const void* omega_inv32, const void* extended_omega32, const void* extended_omega_inv32,
+                                          uint32_t extended_k, void* commits_out);
 B200ZK_API int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count,
                                          uint32_t k, const void* omega_inv32, const void* extended_omega32, uint32_t extended_k,
                                          void* commits_out, void* const* coeff_out_dev, void* const* ext_out_dev, int mode);

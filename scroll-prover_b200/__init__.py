@@ -79,6 +79,7 @@ def _load():
         "b200zk_g_to_lagrange": [vp, vp, u32, vp],
         "b200zk_ntt_fr": [vp, vp, u32, vp, C.c_int, C.c_int],
         "b200zk_ntt_fr_ext": [vp, vp, u32, vp, u32, vp, C.c_int, C.c_int],
+        "b200zk_run_column_jobs": [vp, vp, u32, u32, vp, vp, vp, u32, vp],
         "b200zk_commit_columns": [vp, vp, C.POINTER(vp), u32, u32, vp, vp, u32, vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
         "b200zk_poly_add": [vp, vp, vp, vp, u64],
         "b200zk_poly_sub": [vp, vp, vp, vp, u64],
@@ -110,7 +111,7 @@ ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
-    "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
+    "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
@@ -408,6 +409,35 @@ class Srs:
         if self._h:
             lib().b200zk_srs_release(self.ctx._h, self._h)
             self._h = C.c_void_p()
+
+
+class _ColumnJob(C.Structure):
+    _fields_ = [("host_values", C.c_void_p), ("srs", C.c_void_p), ("mode", C.c_int32), ("coeff_out_dev", C.c_void_p),
+                ("ext_out_dev", C.c_void_p)]
+
+
+def run_column_jobs(ctx: "Context", jobs, k: int, omega_inv=None, extended_omega=None, extended_omega_inv=None,
+                    extended_k: int = 0) -> np.ndarray:
+    """b200zk_run_column_jobs: jobs = [(host_values, srs_or_None, mode, coeff_out_or_None, ext_out_or_None), ...]."""
+    count = len(jobs)
+    arr = (_ColumnJob * max(count, 1))()
+    keep = []
+    for i, (vals, srs, mode, co, eo) in enumerate(jobs):
+        pv, k1 = _ptr(vals)
+        pc, k2 = _ptr(co)
+        pe, k3 = _ptr(eo)
+        keep += [k1, k2, k3]
+        arr[i].host_values = pv.value
+        arr[i].srs = srs._h.value if srs is not None else None
+        arr[i].mode = mode
+        arr[i].coeff_out_dev = pc.value if pc is not None else None
+        arr[i].ext_out_dev = pe.value if pe is not None else None
+    out = np.zeros((count, 12), np.uint64)
+    po, k4 = _ptr(omega_inv)
+    pe1, k5 = _ptr(extended_omega)
+    pe2, k6 = _ptr(extended_omega_inv)
+    ctx._ck(lib().b200zk_run_column_jobs(ctx._h, C.cast(arr, C.c_void_p), count, k, po, pe1, pe2, extended_k, out.ctypes.data))
+    return out
 
 
 def commit_columns(ctx: "Context", srs: "Srs", host_cols, k: int, mode: int = 0, omega_inv=None, extended_omega=None,

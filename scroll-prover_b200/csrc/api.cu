@@ -393,38 +393,51 @@ static int32_t pipeline_init(b200zk_ctx* ctx) {
     return B200ZK_OK;
 }
 
-// One call = the polynomial-arithmetic work create_proof does for `count` columns of 2^k Lagrange values held in
-// HOST memory (pinned for overlap): for each column  commit_lagrange -> lagrange_to_coeff -> (optional)
-// coeff_to_extended, with the H2D copy of column j+1 running on a copy stream while column j computes.
-int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count, uint32_t k,
-                              const void* omega_inv32, const void* extended_omega32, uint32_t extended_k, void* commits_out,
-                              void* const* coeff_out_dev, void* const* ext_out_dev, int mode) {
+// One call = a list of independent per-column jobs of plonk::create_proof whose inputs are in HOST memory (pinned for
+// overlap): the H2D copy of job j+1 runs on a copy stream while job j computes; no host synchronisation inside the loop.
+int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k, const void* omega_inv32,
+                               const void* extended_omega32, const void* extended_omega_inv32, uint32_t extended_k,
+                               void* commits_out) {
     CHECK_CTX(ctx);
-    if ((mode != 3 && !srs) || (count && (!host_cols || (mode != 3 && !commits_out))) || k > 28)
-        return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad arguments");
-    if (mode < 0 || mode > 3) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended), 3 (coeff+extended only)");
-    const bool do_commit = mode != 3, do_ext = mode >= 2;
-    if (mode >= 1 && !omega_inv32) return fail(ctx, B200ZK_E_INVALID, "commit_columns: omega_inv required");
-    if (mode >= 2 && (!extended_omega32 || extended_k < k || extended_k > 28)) return fail(ctx, B200ZK_E_INVALID, "commit_columns: bad extended domain");
-    uint64_t n = 1ull << k;
-    if (mode != 3 && n > srs->n) return fail(ctx, B200ZK_E_INVALID, "commit_columns: 2^k exceeds the SRS length");
+    if (k > 28 || (count && !jobs)) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: bad arguments");
+    const uint64_t n = 1ull << k;
+    bool any_commit = false, any_coeff = false, any_ext = false, any_quot = false;
+    for (uint32_t j = 0; j < count; ++j) {
+        const b200zk_column_job& jb = jobs[j];
+        if (!jb.host_values || jb.mode < 0 || jb.mode > 4) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: job %u malformed", j);
+        if (jb.mode <= 2) {
+            if (!jb.srs || jb.srs->ctx != ctx || n > jb.srs->n)
+                return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: job %u needs an SRS of this context with >= 2^k bases", j);
+            any_commit = true;
+        }
+        any_coeff |= (jb.mode >= 1 && jb.mode <= 3);
+        any_ext |= (jb.mode == 2 || jb.mode == 3);
+        any_quot |= (jb.mode == 4);
+    }
+    if (any_commit && !commits_out) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: commits_out is null");
+    if (any_coeff && !omega_inv32) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: omega_inv required");
+    if ((any_ext && !extended_omega32) || (any_quot && !extended_omega_inv32) || ((any_ext || any_quot) && (extended_k < k || extended_k > 28)))
+        return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: bad extended domain");
     Guard g(ctx);
     if (!count) return B200ZK_OK;
     B2_TRY(pipeline_init(ctx));
-    Fr omega_inv = Fr::one(), ext_omega = Fr::one();
-    if (mode >= 1) B2_TRY(read_fr(ctx, omega_inv32, &omega_inv));
-    if (mode >= 2) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
-    size_t col_bytes = sizeof(Fr) * n;
-    for (int i = 0; i < 2; ++i) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], col_bytes));
+    Fr omega_inv = Fr::one(), ext_omega = Fr::one(), ext_omega_inv = Fr::one();
+    if (any_coeff) B2_TRY(read_fr(ctx, omega_inv32, &omega_inv));
+    if (any_ext) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
+    if (any_quot) B2_TRY(read_fr(ctx, extended_omega_inv32, &ext_omega_inv));
+    const size_t col_bytes = sizeof(Fr) * n, ext_bytes = sizeof(Fr) << extended_k;
+    for (int i = 0; i < 2; ++i) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], any_quot ? ext_bytes : col_bytes));
     B2_TRY(scratch_reserve(ctx, ctx->col_commits, sizeof(Jacobian) * count));
-    if (mode >= 1) B2_TRY(scratch_reserve(ctx, ctx->col_coeff, col_bytes));
-    if (do_ext) B2_TRY(scratch_reserve(ctx, ctx->col_ext, sizeof(Fr) << extended_k));
+    if (any_coeff) B2_TRY(scratch_reserve(ctx, ctx->col_coeff, col_bytes));
+    if (any_ext || any_quot) B2_TRY(scratch_reserve(ctx, ctx->col_ext, ext_bytes));
     Jacobian* commits = (Jacobian*)ctx->col_commits.p;
+    if (any_commit) B2_CUDA(ctx, cudaMemsetAsync(commits, 0, sizeof(Jacobian) * count, ctx->stream));
     bool used[2] = {false, false};
     auto upload = [&](uint32_t j) -> int32_t {
         int b = j & 1;
         if (used[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
-        B2_CUDA(ctx, cudaMemcpyAsync(ctx->colstage[b].p, host_cols[j], col_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        B2_CUDA(ctx, cudaMemcpyAsync(ctx->colstage[b].p, jobs[j].host_values, jobs[j].mode == 4 ? ext_bytes : col_bytes,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
         return B200ZK_OK;
     };
@@ -433,25 +446,48 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
     B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
     B2_TRY(upload(0));
     for (uint32_t j = 0; j < count; ++j) {
+        const b200zk_column_job& jb = jobs[j];
         int b = j & 1;
         if (j + 1 < count) B2_TRY(upload(j + 1));
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
         const Fr* col = (const Fr*)ctx->colstage[b].p;
-        if (do_commit)
-            B2_TRY(msm_run(ctx, (const Affine*)srs->dev_bases, col, n, commits + j, (n * 16 >= srs->n) ? srs->pre_c : 0, srs->n));
-        if (mode >= 1) {
-            Fr* coeff = (coeff_out_dev && coeff_out_dev[j]) ? (Fr*)coeff_out_dev[j] : (Fr*)ctx->col_coeff.p;
+        if (jb.mode <= 2)
+            B2_TRY(msm_run(ctx, (const Affine*)jb.srs->dev_bases, col, n, commits + j, (n * 16 >= jb.srs->n) ? jb.srs->pre_c : 0,
+                           jb.srs->n));
+        if (jb.mode >= 1 && jb.mode <= 3) {
+            Fr* coeff = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_coeff.p;
             B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
-            if (do_ext) {
-                Fr* ext = (ext_out_dev && ext_out_dev[j]) ? (Fr*)ext_out_dev[j] : (Fr*)ctx->col_ext.p;
+            if (jb.mode >= 2) {
+                Fr* ext = jb.ext_out_dev ? (Fr*)jb.ext_out_dev : (Fr*)ctx->col_ext.p;
                 B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
             }
+        } else if (jb.mode == 4) {
+            Fr* out = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_ext.p;
+            B2_TRY(ntt_run(ctx, col, extended_k, out, extended_k, ext_omega_inv, 1, B200ZK_COSET_POST));
         }
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], ctx->stream));
         used[b] = true;
     }
-    if (!do_commit) return B200ZK_OK;
+    if (!any_commit) return B200ZK_OK;
     return deliver(ctx, commits_out, commits, sizeof(Jacobian) * count);
+}
+
+// Homogeneous convenience form: the same mode and SRS for every column.
+int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* host_cols, uint32_t count, uint32_t k,
+                              const void* omega_inv32, const void* extended_omega32, uint32_t extended_k, void* commits_out,
+                              void* const* coeff_out_dev, void* const* ext_out_dev, int mode) {
+    CHECK_CTX(ctx);
+    if (mode < 0 || mode > 3) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended), 3 (coeff+extended only)");
+    if (count && !host_cols) return fail(ctx, B200ZK_E_INVALID, "commit_columns: null host_cols");
+    std::vector<b200zk_column_job> jobs(count);
+    for (uint32_t j = 0; j < count; ++j) {
+        jobs[j].host_values = host_cols[j];
+        jobs[j].srs = srs;
+        jobs[j].mode = mode;
+        jobs[j].coeff_out_dev = coeff_out_dev ? coeff_out_dev[j] : nullptr;
+        jobs[j].ext_out_dev = ext_out_dev ? ext_out_dev[j] : nullptr;
+    }
+    return b200zk_run_column_jobs(ctx, jobs.data(), count, k, omega_inv32, extended_omega32, nullptr, extended_k, commits_out);
 }
 
 // ---- poly ops ------------------------------------------------------------------------------------

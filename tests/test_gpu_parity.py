@@ -385,6 +385,21 @@ def test_commit_columns_pipeline_matches_oracle(ctx, zk):
         assert np.array_equal(ext_out[i].cpu().numpy().view(np.uint64), dom_o.coeff_to_extended(ce, threads=4)), i
     only = zk.commit_columns(ctx, srs, cols, k, mode=0)
     assert np.array_equal(only, commits)
+    # heterogeneous job list in one call: commit-only, transforms-only (mode 3) and the quotient job (mode 4)
+    ext_h = dom_o.coeff_to_extended(dom_o.lagrange_to_coeff(cols[1], threads=4), threads=4)
+    c3 = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    e3 = torch.empty((4 * n, 4), dtype=torch.int64, device="cuda")
+    q4 = torch.empty((4 * n, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    res = zk.run_column_jobs(ctx, [(cols[0], srs, 0, None, None), (cols[2], None, 3, c3, e3), (ext_h, None, 4, q4, None),
+                                   (cols[4], srs, 1, None, None)], k, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
+                             extended_omega_inv=dom.extended_omega_inv, extended_k=k + 2)
+    ctx.synchronize()
+    assert np.array_equal(res[0], commits[0]) and np.array_equal(res[3], commits[4]) and not res[1].any() and not res[2].any()
+    ce2 = dom_o.lagrange_to_coeff(cols[2], threads=4)
+    assert np.array_equal(c3.cpu().numpy().view(np.uint64), ce2)
+    assert np.array_equal(e3.cpu().numpy().view(np.uint64), dom_o.coeff_to_extended(ce2, threads=4))
+    assert np.array_equal(q4.cpu().numpy().view(np.uint64), dom_o.extended_to_coeff(ext_h, threads=4))
     srs.release()
 
 
