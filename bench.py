@@ -267,67 +267,54 @@ def run_b200(args):
     ctx.g1_generator_mul_batch(rand_limbs(n), out=gl)
     params = zk.ParamsKZG(ctx, k, g, gl)
     del g, gl, srs_scalars
-    coeff = torch.empty((n, 4), dtype=torch.int64, device=dev)
-    ext = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev)
-    hwork = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev)
     my_jobs = assign_jobs(make_jobs(), world)[rank]
     n_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
-    commits = np.zeros((max(n_msm, 1), 12), np.uint64)
+    commits = np.zeros((len(my_jobs) + 1, 12), np.uint64)
     msm_units = {"adds": 0, "nw": 0}
-
-    def do_job(job, idx, src):
-        kind = job[0]
-        if kind == "lmsm":
-            commits[idx] = params.commit_lagrange(src)
-        elif kind == "ntt":
-            ctx.ntt_ext(src, k, coeff, k, dom.omega_inv, True, zk.COSET_NONE)
-            ctx.ntt_ext(coeff, k, ext, ek, dom.extended_omega, False, zk.COSET_PRE)
-        elif kind == "msm":
-            commits[idx] = params.commit(src)
-        else:
-            ctx.ntt_ext(src, ek, hwork, ek, dom.extended_omega_inv, True, zk.COSET_POST)
-
-    def src_for(job, j):
-        return hext if job[0] == "icoset" else cols[job[1]][j % 2]
-
-    def step_resident():
-        mi = 0
-        for j, job in enumerate(my_jobs):
-            do_job(job, mi, src_for(job, j))
-            if job[0] in ("lmsm", "msm"):
-                mi += 1
-
-    # ---- e2e: host (pinned) columns -> session API; H2D of job j+1 overlaps compute of job j
-    host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
-            "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
-    hstage = torch.empty((1 << ek, 4), dtype=torch.int64, device=dev) if host["h"] is not None else None
-    # a column whose commitment and transforms are on the same rank crosses PCIe once (one mode-2 call)
-    _nl, _nn = sum(1 for j in my_jobs if j[0] == "lmsm"), sum(1 for j in my_jobs if j[0] == "ntt")
-    h2d_bytes = (max(_nl, _nn) + sum(1 for j in my_jobs if j[0] == "msm")) * n * 32 + \
-        sum((1 << ek) * 32 for j in my_jobs if j[0] == "icoset")
-    d2h_bytes = n_msm * 96
 
     lmsm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "lmsm"]
     ntt_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "ntt"]
     msm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "msm"]
     has_icoset = any(job[0] == "icoset" for job in my_jobs)
 
-    def step_e2e():
-        """Everything through the C ABI with HOST (pinned) buffers: b200zk_commit_columns double-buffers the H2D of
-        column j+1 on its copy stream against the kernels of column j; commitments are read back (D2H) per call."""
-        # ONE b200zk_run_column_jobs call for everything this rank owns: a column whose commitment and transforms both
-        # landed here is uploaded once (mode 2); the quotient's extended_to_coeff is a mode-4 job of the same pipeline
+    def job_list(src, hsrc):
+        """Everything this rank owns as ONE b200zk_run_column_jobs list: a column whose commitment and transforms both
+        landed here is one mode-2 job (uploaded once in the e2e arm); the quotient's extended_to_coeff is a mode-4 job."""
         both = min(len(lmsm_jobs), len(ntt_jobs))
-        jl = [(host[job[1]][j % 2], params._gl, 2, None, None) for j, job in lmsm_jobs[:both]]
-        jl += [(host[job[1]][j % 2], params._gl, 0, None, None) for j, job in lmsm_jobs[both:]]
-        jl += [(host[job[1]][j % 2], None, 3, None, None) for j, job in ntt_jobs[both:]]
-        jl += [(host[job[1]][j % 2], params._g, 0, None, None) for j, job in msm_jobs]
+        jl = [(src[job[1]][j % 2], params._gl, 2, None, None) for j, job in lmsm_jobs[:both]]
+        jl += [(src[job[1]][j % 2], params._gl, 0, None, None) for j, job in lmsm_jobs[both:]]
+        jl += [(src[job[1]][j % 2], None, 3, None, None) for j, job in ntt_jobs[both:]]
+        jl += [(src[job[1]][j % 2], params._g, 0, None, None) for j, job in msm_jobs]
         if has_icoset:
-            jl.append((host["h"], None, 4, None, None))
+            jl.append((hsrc, None, 4, None, None))
+        return jl
+
+    def run_jobs(jl):
         if jl:
-            zk.run_column_jobs(ctx, jl, k, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
-                               extended_omega_inv=dom.extended_omega_inv, extended_k=ek)
+            commits[: len(jl)] = zk.run_column_jobs(ctx, jl, k, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
+                                                    extended_omega_inv=dom.extended_omega_inv, extended_k=ek)
         torch.cuda.current_stream().synchronize()
+
+    resident_jobs = job_list(cols, hext)
+
+    def step_resident():
+        """inputs already resident in HBM; the library runs the commitments and the transforms on two streams"""
+        run_jobs(resident_jobs)
+
+    # ---- e2e: host (pinned) columns -> session API; H2D of job j+1 overlaps compute of job j
+    host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
+            "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
+    # a column whose commitment and transforms are on the same rank crosses PCIe once (one mode-2 call)
+    _nl, _nn = sum(1 for j in my_jobs if j[0] == "lmsm"), sum(1 for j in my_jobs if j[0] == "ntt")
+    h2d_bytes = (max(_nl, _nn) + sum(1 for j in my_jobs if j[0] == "msm")) * n * 32 + \
+        sum((1 << ek) * 32 for j in my_jobs if j[0] == "icoset")
+    d2h_bytes = n_msm * 96
+
+    host_jobs = job_list(host, host["h"])
+
+    def step_e2e():
+        """the same job list from pinned HOST buffers: H2D of job j+1 on the library's copy stream while job j computes"""
+        run_jobs(host_jobs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -338,8 +325,8 @@ def run_b200(args):
     def gather_commits():
         if not dist:
             return
-        t = torch.zeros((world, 40, 12), dtype=torch.int64, device=dev)
-        mine = torch.zeros((40, 12), dtype=torch.int64, device=dev)
+        t = torch.zeros((world, 80, 12), dtype=torch.int64, device=dev)
+        mine = torch.zeros((80, 12), dtype=torch.int64, device=dev)
         mine[: len(commits)] = torch.from_numpy(commits.view(np.int64)).to(dev)
         dist.all_gather_into_tensor(t.view(-1), mine.view(-1))
 

@@ -76,6 +76,7 @@ int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out) {
         return B200ZK_E_CUDA;
     }
     ctx->own_stream = true;
+    if (const char* e = getenv("B200ZK_OVERLAP")) ctx->overlap = atoi(e);
     if (const char* e = getenv("B200ZK_ACC_L")) ctx->msm_acc_l = (uint32_t)atoi(e);
     if (const char* e = getenv("B200ZK_SCATTER_SWEEPS")) ctx->msm_scatter_sweeps = (uint32_t)atoi(e);  // experiment knob
     if (cudaMalloc(&ctx->msm_adds_dev, 8) == cudaSuccess) cudaMemset(ctx->msm_adds_dev, 0, 8);
@@ -98,8 +99,12 @@ int32_t b200zk_ctx_destroy(b200zk_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+        if (ctx->ev_used_aux[i]) cudaEventDestroy(ctx->ev_used_aux[i]);
     }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B200ZK_OK;
@@ -386,10 +391,14 @@ int32_t b200zk_ntt_fr(b200zk_ctx* ctx, void* data, uint32_t log_n, const void* o
 static int32_t pipeline_init(b200zk_ctx* ctx) {
     if (ctx->copy_stream) return B200ZK_OK;
     B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
         B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_used_aux[i], cudaEventDisableTiming));
     }
+    B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     return B200ZK_OK;
 }
 
@@ -432,41 +441,87 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
     if (any_ext || any_quot) B2_TRY(scratch_reserve(ctx, ctx->col_ext, ext_bytes));
     Jacobian* commits = (Jacobian*)ctx->col_commits.p;
     if (any_commit) B2_CUDA(ctx, cudaMemsetAsync(commits, 0, sizeof(Jacobian) * count, ctx->stream));
-    bool used[2] = {false, false};
+
+    // Two compute streams: the commitments (MSM) run on the context stream, the transforms of the same column on
+    // aux_stream.  Only msm_accumulate and the NTT passes are bound by the INT32 pipe; the MSM's sort / reduction phases
+    // are latency- or memory-bound and overlap with the other stream's butterflies.
+    const bool overlap = ctx->overlap && (any_coeff || any_quot) && any_commit;
+    cudaStream_t main_stream = ctx->stream, ntt_stream = overlap ? ctx->aux_stream : ctx->stream;
+    struct StreamSwap {  // ntt_run / msm_run launch on ctx->stream
+        b200zk_ctx* c;
+        cudaStream_t saved;
+        StreamSwap(b200zk_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+        ~StreamSwap() { c->stream = saved; }
+    };
+    if (any_coeff) {  // twiddle tables are built once, on the context stream, before the streams fork
+        const Fr* t = nullptr;
+        B2_TRY(ntt_get_table(ctx, omega_inv, k, &t));
+    }
+    if (any_ext && extended_k >= 1) {
+        const Fr* t = nullptr;
+        B2_TRY(ntt_get_table(ctx, ext_omega, extended_k, &t));
+    }
+    if (any_quot && extended_k >= 1) {
+        const Fr* t = nullptr;
+        B2_TRY(ntt_get_table(ctx, ext_omega_inv, extended_k, &t));
+    }
+    // neither the copy stream nor the aux stream may overtake work already queued on the context stream
+    B2_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+    B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    if (overlap) B2_CUDA(ctx, cudaStreamWaitEvent(ntt_stream, ctx->ev_fork, 0));
+
+    bool used_main[2] = {false, false}, used_aux[2] = {false, false};
+    auto is_dev = [&](uint32_t j) { return is_device_ptr(jobs[j].host_values); };
     auto upload = [&](uint32_t j) -> int32_t {
+        if (is_dev(j)) return B200ZK_OK;  // already resident: used in place
         int b = j & 1;
-        if (used[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
+        if (used_main[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
+        if (used_aux[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used_aux[b], 0));
         B2_CUDA(ctx, cudaMemcpyAsync(ctx->colstage[b].p, jobs[j].host_values, jobs[j].mode == 4 ? ext_bytes : col_bytes,
                                      cudaMemcpyHostToDevice, ctx->copy_stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
         return B200ZK_OK;
     };
-    // the copy stream must not overtake work already queued on the compute stream that still reads the stage buffers
-    B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
-    B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
     B2_TRY(upload(0));
     for (uint32_t j = 0; j < count; ++j) {
         const b200zk_column_job& jb = jobs[j];
-        int b = j & 1;
+        const int b = j & 1;
+        const bool dev_in = is_dev(j);
         if (j + 1 < count) B2_TRY(upload(j + 1));
-        B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        const Fr* col = (const Fr*)ctx->colstage[b].p;
-        if (jb.mode <= 2)
+        const Fr* col = dev_in ? (const Fr*)jb.host_values : (const Fr*)ctx->colstage[b].p;
+        const bool has_msm = jb.mode <= 2, has_ntt = jb.mode >= 1;
+        if (has_msm) {
+            if (!dev_in) B2_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_copied[b], 0));
             B2_TRY(msm_run(ctx, (const Affine*)jb.srs->dev_bases, col, n, commits + j, (n * 16 >= jb.srs->n) ? jb.srs->pre_c : 0,
                            jb.srs->n));
-        if (jb.mode >= 1 && jb.mode <= 3) {
-            Fr* coeff = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_coeff.p;
-            B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
-            if (jb.mode >= 2) {
-                Fr* ext = jb.ext_out_dev ? (Fr*)jb.ext_out_dev : (Fr*)ctx->col_ext.p;
-                B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
+            if (!dev_in) {
+                B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], main_stream));
+                used_main[b] = true;
             }
-        } else if (jb.mode == 4) {
-            Fr* out = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_ext.p;
-            B2_TRY(ntt_run(ctx, col, extended_k, out, extended_k, ext_omega_inv, 1, B200ZK_COSET_POST));
         }
-        B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], ctx->stream));
-        used[b] = true;
+        if (has_ntt) {
+            StreamSwap sw(ctx, ntt_stream);
+            if (!dev_in) B2_CUDA(ctx, cudaStreamWaitEvent(ntt_stream, ctx->ev_copied[b], 0));
+            if (jb.mode <= 3) {
+                Fr* coeff = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_coeff.p;
+                B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
+                if (jb.mode >= 2) {
+                    Fr* ext = jb.ext_out_dev ? (Fr*)jb.ext_out_dev : (Fr*)ctx->col_ext.p;
+                    B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
+                }
+            } else {
+                Fr* out = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_ext.p;
+                B2_TRY(ntt_run(ctx, col, extended_k, out, extended_k, ext_omega_inv, 1, B200ZK_COSET_POST));
+            }
+            if (!dev_in) {
+                B2_CUDA(ctx, cudaEventRecord(overlap ? ctx->ev_used_aux[b] : ctx->ev_used[b], ntt_stream));
+                (overlap ? used_aux : used_main)[b] = true;
+            }
+        }
+    }
+    if (overlap) {  // join: everything issued on the aux stream is ordered before later work on the context stream
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_join, ntt_stream));
+        B2_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
     }
     if (!any_commit) return B200ZK_OK;
     return deliver(ctx, commits_out, commits, sizeof(Jacobian) * count);

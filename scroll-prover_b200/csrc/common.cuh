@@ -62,6 +62,9 @@ struct b200zk_ctx {
     std::vector<b200zk::TwiddleTable> tables;
     // column pipeline (b200zk_commit_columns): copy stream + double-buffered staging
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // transforms of a column run here, concurrently with its MSM on `stream`
+    cudaEvent_t ev_used_aux[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;                       // B200ZK_OVERLAP=0 serialises MSM and transforms on one stream
     b200zk::Scratch colstage[2], col_coeff, col_ext, col_commits;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     // profiling
