@@ -128,6 +128,9 @@ B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t l
  *           multi-GPU caller place a column's MSM and its transforms on different ranks
  * commits_out: count x 96 B normalised Jacobian points (host or device).  No host synchronisation inside the loop;
  * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs. */
+/* on (default): inside b200zk_run_column_jobs the commitments run on the context stream and the transforms on a second
+ * stream, so the MSM's latency/memory-bound phases overlap with NTT butterflies; off: one stream (per-kernel timing). */
+B200ZK_API int32_t b200zk_ctx_set_overlap(b200zk_ctx* ctx, int on);
 /* Heterogeneous form: every job names its own host buffer, SRS and mode, so one proof phase (Lagrange commits,
  * coefficient-form commits, transforms, and the quotient's extended_to_coeff) is ONE call with a full copy/compute pipeline:
  *   mode 0..3 as above (host_values holds 2^k elements);

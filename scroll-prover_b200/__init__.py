@@ -79,6 +79,7 @@ def _load():
         "b200zk_g_to_lagrange": [vp, vp, u32, vp],
         "b200zk_ntt_fr": [vp, vp, u32, vp, C.c_int, C.c_int],
         "b200zk_ntt_fr_ext": [vp, vp, u32, vp, u32, vp, C.c_int, C.c_int],
+        "b200zk_ctx_set_overlap": [vp, C.c_int],
         "b200zk_run_column_jobs": [vp, vp, u32, u32, vp, vp, vp, u32, vp],
         "b200zk_commit_columns": [vp, vp, C.POINTER(vp), u32, u32, vp, vp, u32, vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
         "b200zk_poly_add": [vp, vp, vp, vp, u64],
@@ -111,7 +112,7 @@ ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
-    "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
+    "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
@@ -191,6 +192,9 @@ class Context:
         pd, k1 = _ptr(dev)
         ph, k2 = _ptr(host)
         self._ck(lib().b200zk_buf_upload(self._h, pd, ph, nbytes))
+
+    def set_overlap(self, on: bool):
+        self._ck(lib().b200zk_ctx_set_overlap(self._h, int(on)))
 
     def launch_count(self) -> int:
         v = C.c_uint64()

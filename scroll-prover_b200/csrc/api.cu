@@ -692,6 +692,12 @@ int32_t b200zk_profile_read(b200zk_ctx* ctx, const char* name, double* total_ms,
     return fail(ctx, B200ZK_E_INVALID, "profile_read: unknown kernel class '%s'", name);
 }
 
+int32_t b200zk_ctx_set_overlap(b200zk_ctx* ctx, int on) {
+    CHECK_CTX(ctx);
+    Guard g(ctx);
+    ctx->overlap = on != 0;
+    return B200ZK_OK;
+}
 int32_t b200zk_srs_set_precompute(b200zk_ctx* ctx, int mode) {
     CHECK_CTX(ctx);
     if (mode != 0 && mode != 1) return fail(ctx, B200ZK_E_INVALID, "srs_set_precompute: mode must be 0 or 1");
