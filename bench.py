@@ -230,7 +230,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     k, n, ek = args.k, 1 << args.k, args.k + 2
-    comp, copy = torch.cuda.Stream(), torch.cuda.Stream()
+    comp = torch.cuda.Stream()  # a non-default stream, so that our CUDA events bracket the library's launches
     torch.cuda.set_stream(comp)
     ctx = zk.Context(local)
     ctx.set_stream(comp.cuda_stream)
@@ -270,7 +270,6 @@ def run_b200(args):
     my_jobs = assign_jobs(make_jobs(), world)[rank]
     n_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
     commits = np.zeros((len(my_jobs) + 1, 12), np.uint64)
-    msm_units = {"adds": 0, "nw": 0}
 
     lmsm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "lmsm"]
     ntt_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "ntt"]
@@ -308,9 +307,9 @@ def run_b200(args):
     _nl, _nn = sum(1 for j in my_jobs if j[0] == "lmsm"), sum(1 for j in my_jobs if j[0] == "ntt")
     h2d_bytes = (max(_nl, _nn) + sum(1 for j in my_jobs if j[0] == "msm")) * n * 32 + \
         sum((1 << ek) * 32 for j in my_jobs if j[0] == "icoset")
-    d2h_bytes = n_msm * 96
 
     host_jobs = job_list(host, host["h"])
+    d2h_bytes = len(host_jobs) * 96  # the commitments array of the one run_column_jobs call
 
     def step_e2e():
         """the same job list from pinned HOST buffers: H2D of job j+1 on the library's copy stream while job j computes"""
