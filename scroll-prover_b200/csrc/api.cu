@@ -76,7 +76,6 @@ int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out) {
         return B200ZK_E_CUDA;
     }
     ctx->own_stream = true;
-    if (const char* e = getenv("B200ZK_PARTITION_SORT")) ctx->msm_partition_sort = atoi(e);
     if (const char* e = getenv("B200ZK_OVERLAP")) ctx->overlap = atoi(e);
     if (const char* e = getenv("B200ZK_ACC_L")) ctx->msm_acc_l = (uint32_t)atoi(e);
     if (const char* e = getenv("B200ZK_SCATTER_SWEEPS")) ctx->msm_scatter_sweeps = (uint32_t)atoi(e);  // experiment knob

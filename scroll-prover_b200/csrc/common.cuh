@@ -77,7 +77,6 @@ struct b200zk_ctx {
     uint32_t msm_window = 0;
     uint32_t msm_scatter_sweeps = 0;
     uint32_t msm_acc_l = 0;
-    int msm_partition_sort = 0;  // B200ZK_PARTITION_SORT=1: two-pass partitioned counting sort for large MSMs (experiment)
     int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;

@@ -29,7 +29,7 @@ static constexpr uint32_t PART_INVALID = 0x1fffffffu;  // also the bucket-id mas
 static constexpr uint32_t PART_GIANT = 0x20000000u;
 static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
-static constexpr int ACC_L_DEFAULT = 128;  // sorted entries per accumulate thread (B200ZK_ACC_L overrides, experiments)
+static constexpr int ACC_L_DEFAULT = 256;  // sorted entries per accumulate thread (B200ZK_ACC_L overrides, experiments)
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -111,55 +111,6 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
         uint32_t i = (uint32_t)(idx - w * n);
         uint32_t pos = atomicAdd(&cursor[(pl.Ws == 1 ? 0ull : w * pl.B) + (d & 0x7fffffffu) - 1], 1u);
         entries[pos] = (uint32_t)(i + w * pl.stride) | (d & 0x80000000u);
-    }
-}
-
-// ---- two-pass partitioned counting sort (used for large single-bucket-set MSMs) --------------------------------
-// Pass 1 splits the digits into PART_BINS coarse bins of consecutive buckets (bin regions are known from the fine
-// offsets), writing (bucket, entry) pairs: each block counts its chunk per bin in shared memory, reserves one
-// contiguous run per bin with a single global atomic and then writes its pairs there, so the stores are short
-// sequential runs instead of random 4-byte scatters.  Pass 2 walks the pairs (grouped by bin) and finishes the counting
-// sort inside the bin, whose cursor block and entry region are a few MB and stay L2-resident.
-static constexpr uint32_t PART_BINS = 256, PART_CHUNK = 8192;
-
-__global__ void __launch_bounds__(256) msm_partition(const uint32_t* __restrict__ digits, uint64_t n, MsmPlan pl, uint32_t sh,
-                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ bin_cursor,
-                                                     uint2* __restrict__ pairs) {
-    __shared__ uint32_t cnt[PART_BINS], base[PART_BINS];
-    const uint64_t total = n * pl.W;
-    const uint64_t c0 = (uint64_t)blockIdx.x * PART_CHUNK;
-    const uint64_t c1 = c0 + PART_CHUNK < total ? c0 + PART_CHUNK : total;
-    for (uint32_t t = threadIdx.x; t < PART_BINS; t += blockDim.x) cnt[t] = 0;
-    __syncthreads();
-    for (uint64_t idx = c0 + threadIdx.x; idx < c1; idx += blockDim.x) {
-        uint32_t d = digits[idx];
-        if (d) atomicAdd(&cnt[((d & 0x7fffffffu) - 1) >> sh], 1u);
-    }
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < PART_BINS; t += blockDim.x) {
-        uint32_t c = cnt[t];
-        base[t] = c ? offsets[(uint64_t)t << sh] + atomicAdd(&bin_cursor[t], c) : 0;
-        cnt[t] = 0;
-    }
-    __syncthreads();
-    for (uint64_t idx = c0 + threadIdx.x; idx < c1; idx += blockDim.x) {
-        uint32_t d = digits[idx];
-        if (!d) continue;
-        uint32_t bk = (d & 0x7fffffffu) - 1, bin = bk >> sh;
-        uint32_t r = atomicAdd(&cnt[bin], 1u);
-        uint64_t w = idx / n;
-        uint32_t i = (uint32_t)(idx - w * n);
-        pairs[base[bin] + r] = make_uint2(bk, (uint32_t)(i + w * pl.stride) | (d & 0x80000000u));
-    }
-}
-
-__global__ void __launch_bounds__(256) msm_partition_finish(const uint2* __restrict__ pairs, const uint32_t* __restrict__ total_entries,
-                                                            uint32_t* cursor, uint32_t* entries) {
-    const uint32_t M = *total_entries;
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += stride) {
-        uint2 e = pairs[p];
-        entries[atomicAdd(&cursor[e.x], 1u)] = e.y;
     }
 }
 
@@ -616,9 +567,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     size_t o_flag = carve(256);
     size_t o_entries = carve(4 * (max_entries + 4));
     size_t o_digits = carve(4 * (max_entries + 4));
-    // two-pass partitioned sort: one bucket set of >= 2^16 buckets and enough entries to be worth the extra pass
-    const bool partitioned = ctx->msm_partition_sort && pl.Ws == 1 && pl.B >= (1u << 16) && max_entries >= (1ull << 22);
-    size_t o_pairs = carve(partitioned ? 8 * (max_entries + 4) : 16), o_bincur = carve(4 * PART_BINS);
     size_t o_buckets = carve(sizeof(XYZZ) * pl.NB);
     size_t o_pid = carve(4 * 2 * nthreads), o_pval = carve(sizeof(XYZZ) * 2 * nthreads);
     uint64_t nthreads2 = (2 * nthreads + COMBINE_LR - 1) / COMBINE_LR;
@@ -636,8 +584,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     uint32_t* giant_flag = (uint32_t*)(base + o_flag);
     uint32_t* entries = (uint32_t*)(base + o_entries);
     uint32_t* digits = (uint32_t*)(base + o_digits);
-    uint2* pairs = (uint2*)(base + o_pairs);
-    uint32_t* bin_cursor = (uint32_t*)(base + o_bincur);
     uint32_t* pid2 = (uint32_t*)(base + o_pid2);
     XYZZ* pval2 = (XYZZ*)(base + o_pval2);
     XYZZ* buckets = (XYZZ*)(base + o_buckets);
@@ -675,15 +621,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             ProfScope ps_(ctx, PROF_MSM_SCATTER);
             uint64_t want = (max_entries + 1023) / 1024;  // 4 digits per thread, blocks issued in window-major order
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
-            if (partitioned) {
-                uint32_t sh = 0;
-                while ((pl.B >> sh) > PART_BINS) ++sh;  // B / 2^sh = PART_BINS coarse bins of consecutive buckets
-                B2_CUDA(ctx, cudaMemsetAsync(bin_cursor, 0, 4 * PART_BINS, st));
-                uint64_t pblocks = (max_entries + PART_CHUNK - 1) / PART_CHUNK;
-                msm_partition<<<(uint32_t)pblocks, 256, 0, st>>>(digits, n, pl, sh, offsets, bin_cursor, pairs);
-                B2_LAUNCH_CHECK(ctx);
-                msm_partition_finish<<<(uint32_t)ctx->sm_count * 8, 256, 0, st>>>(pairs, offsets + pl.NB, cursor, entries);
-            } else {
+            {
                 uint32_t sweeps = 1;
                 if (pl.Ws == 1) {
                     // measured on B200 at n = 2^24 (805 MB of entries): 1 sweep 6.3 ms, 2: 4.9, 4: 4.1, 16: 11.5 -- each
