@@ -165,6 +165,89 @@ B200ZK_API int32_t b200zk_batch_invert(b200zk_ctx* ctx, void* data, uint64_t n);
 /* arithmetic::kate_division: q (n-1 coeffs) = a (n coeffs) / (X - b) */
 B200ZK_API int32_t b200zk_kate_division(b200zk_ctx* ctx, void* q, const void* a, uint64_t n, const void* b32);
 
+/* ---- quotient construction: the work of create_proof BETWEEN the transforms ------------------
+ * Upstream: halo2_proofs/src/plonk/{evaluation.rs, permutation/prover.rs, mv_lookup/prover.rs} @ e5ddf67 (pin
+ * /root/reference/Cargo.lock:1886-1888; entered from /root/reference/integration/src/prove.rs:37-39).  All column
+ * arguments of this group are DEVICE pointers (columns stay resident between b200zk_run_column_jobs and here);
+ * scalars, programs and pointer tables are host memory. */
+
+/* Exclusive running product / sum with an initial value: out[0] = init, out[i] = out[i-1] (*|+) in[i-1], i < n.
+ * This is the z(X) loop of permutation::Argument::commit (op 0) and the phi(X) loop of the log-derivative lookup
+ * (op 1).  in == out is allowed. */
+#define B200ZK_SCAN_PRODUCT 0
+#define B200ZK_SCAN_SUM 1
+B200ZK_API int32_t b200zk_prefix_scan(b200zk_ctx* ctx, int op, const void* in_dev, uint64_t n, const void* init32, void* out_dev);
+
+/* One column set of the permutation argument (permutation::Argument::commit, one iteration of its chunk loop):
+ *   mv[i]  = prod_j (beta * sigma_j[i] + gamma + v_j[i])            (denominators, then ff::BatchInvert)
+ *   mv[i] *= prod_j (delta_omega_j * omega^i * beta + gamma + v_j[i]),  delta_omega_j = delta_omega_start * delta^j
+ *   z[0] = z_init, z[i] = z[i-1] * mv[i-1]                          (i < 2^k)
+ * values_dev / sigma_dev: n_cols device columns of 2^k Lagrange values each.  The caller overwrites the blinding rows
+ * and reads z[2^k - (blinding_factors + 1)] as the next set's z_init, exactly as upstream does on the host. */
+B200ZK_API int32_t b200zk_permutation_product(b200zk_ctx* ctx, const void* const* values_dev, const void* const* sigma_dev,
+                                              uint32_t n_cols, const void* beta32, const void* gamma32,
+                                              const void* delta_omega_start32, const void* delta32, const void* omega32,
+                                              uint32_t k, const void* z_init32, void* z_out_dev);
+
+/* Running sum of the log-derivative lookup (mv_lookup::prover, the phi(X) column):
+ *   d[i] = sum_j 1 / (inputs_j[i] + beta)  -  m[i] / (table[i] + beta);   phi[0] = phi_init, phi[i] = phi[i-1] + d[i-1]
+ * inputs_dev: n_inputs compressed input columns; table_dev: compressed table column; m_dev: multiplicities.
+ * Zero denominators invert to zero, as ff::BatchInvert leaves them. */
+B200ZK_API int32_t b200zk_logup_running_sum(b200zk_ctx* ctx, const void* const* inputs_dev, uint32_t n_inputs,
+                                            const void* table_dev, const void* m_dev, const void* beta32, uint32_t k,
+                                            const void* phi_init32, void* phi_out_dev);
+
+/* plonk::evaluation::GraphEvaluator on the device.  A program is the upstream `calculations` list: calculation i
+ * writes intermediate i; operands are ValueSources.  Calculation::Horner(start, parts, factor) names its parts as a
+ * range of `horner_parts`.  B200ZK_SRC_EXTENDED_X is an addition over upstream: the point zeta * extended_omega^row of
+ * the extended coset, so that the permutation / lookup identities (hard-coded loops upstream) are programs too. */
+#define B200ZK_SRC_CONSTANT 0u       /* index into the program's constants */
+#define B200ZK_SRC_INTERMEDIATE 1u   /* index of an earlier calculation */
+#define B200ZK_SRC_FIXED 2u          /* index = column, rotation = index into the program's rotations */
+#define B200ZK_SRC_ADVICE 3u
+#define B200ZK_SRC_INSTANCE 4u
+#define B200ZK_SRC_CHALLENGE 5u      /* index into challenges */
+#define B200ZK_SRC_BETA 6u
+#define B200ZK_SRC_GAMMA 7u
+#define B200ZK_SRC_THETA 8u
+#define B200ZK_SRC_Y 9u
+#define B200ZK_SRC_PREVIOUS_VALUE 10u
+#define B200ZK_SRC_EXTENDED_X 11u
+#define B200ZK_CALC_ADD 0u
+#define B200ZK_CALC_SUB 1u
+#define B200ZK_CALC_MUL 2u
+#define B200ZK_CALC_SQUARE 3u
+#define B200ZK_CALC_DOUBLE 4u
+#define B200ZK_CALC_NEGATE 5u
+#define B200ZK_CALC_HORNER 6u        /* a = start value, b = factor, parts = horner_parts[parts_offset .. +parts_len] */
+#define B200ZK_CALC_STORE 7u
+typedef struct b200zk_value_source {
+    uint32_t kind, index, rotation;
+} b200zk_value_source;
+typedef struct b200zk_calculation {
+    uint32_t op;
+    b200zk_value_source a, b;
+    uint32_t parts_offset, parts_len;
+} b200zk_calculation;
+typedef struct b200zk_graph b200zk_graph;
+/* Validates the program, assigns the live intermediates to on-chip slots and uploads the instruction stream. */
+B200ZK_API int32_t b200zk_graph_create(b200zk_ctx* ctx, const b200zk_calculation* calculations, uint32_t n_calculations,
+                                       const b200zk_value_source* horner_parts, uint32_t n_parts, const void* constants32,
+                                       uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations,
+                                       b200zk_graph** out);
+B200ZK_API int32_t b200zk_graph_destroy(b200zk_ctx* ctx, b200zk_graph* graph);
+B200ZK_API int32_t b200zk_graph_info(const b200zk_graph* graph, uint32_t* n_instructions, uint32_t* n_slots);
+/* GraphEvaluator::evaluate for every row of the extended domain: values[row] = result of the last calculation, with
+ * PreviousValue = the old values[row] (so successive programs chain the way evaluate_h folds gates with y) and
+ * column reads at (row + rotations[r] * rot_scale) mod 2^log_size.  extended_omega32 is only read when the program
+ * uses B200ZK_SRC_EXTENDED_X (may be NULL otherwise). */
+B200ZK_API int32_t b200zk_graph_evaluate(b200zk_ctx* ctx, const b200zk_graph* graph, const void* const* fixed_dev,
+                                         uint32_t n_fixed, const void* const* advice_dev, uint32_t n_advice,
+                                         const void* const* instance_dev, uint32_t n_instance, const void* challenges32,
+                                         uint32_t n_challenges, const void* beta32, const void* gamma32, const void* theta32,
+                                         const void* y32, const void* extended_omega32, void* values_dev, uint32_t log_size,
+                                         int32_t rot_scale);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* element-wise Fr/Fq Montgomery product of two arrays on the device (field-layer parity tests) */
 B200ZK_API int32_t b200zk_debug_field_op(b200zk_ctx* ctx, int field /*0 Fr,1 Fq*/, int op /*0 mul,1 add,2 sub,3 inv*/,

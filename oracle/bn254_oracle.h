@@ -105,6 +105,31 @@ void halo2_params_setup(uint32_t k, const fr_t *tau, g1_affine_t *g, g1_affine_t
 void halo2_g_to_lagrange(const g1_affine_t *g, g1_affine_t *g_lagrange, uint32_t k, int threads);
 void halo2_commit(const g1_affine_t *bases, const fr_t *poly, uint64_t n, int threads, g1_t *out);
 
+/* ---- halo2_proofs::plonk quotient construction (halo2_quotient.c) ---- */
+/* plonk::evaluation::{ValueSource, Calculation} in upstream declaration order (+ ExtendedX, see halo2_quotient.c) */
+enum { HALO2_SRC_CONSTANT = 0, HALO2_SRC_INTERMEDIATE, HALO2_SRC_FIXED, HALO2_SRC_ADVICE, HALO2_SRC_INSTANCE,
+       HALO2_SRC_CHALLENGE, HALO2_SRC_BETA, HALO2_SRC_GAMMA, HALO2_SRC_THETA, HALO2_SRC_Y, HALO2_SRC_PREVIOUS_VALUE,
+       HALO2_SRC_EXTENDED_X };
+enum { HALO2_CALC_ADD = 0, HALO2_CALC_SUB, HALO2_CALC_MUL, HALO2_CALC_SQUARE, HALO2_CALC_DOUBLE, HALO2_CALC_NEGATE,
+       HALO2_CALC_HORNER, HALO2_CALC_STORE };
+typedef struct { uint32_t kind, index, rotation; } halo2_value_source_t;
+typedef struct {
+    uint32_t op;
+    halo2_value_source_t a, b; /* Horner: a = start value, b = factor */
+    uint32_t parts_offset, parts_len;
+} halo2_calculation_t;
+int halo2_graph_evaluate(const halo2_calculation_t *calcs, uint32_t n_calcs, const halo2_value_source_t *parts,
+                         const fr_t *constants, const int32_t *rotations, uint32_t n_rotations, const fr_t *const *fixed,
+                         const fr_t *const *advice, const fr_t *const *instance, const fr_t *challenges, const fr_t *beta,
+                         const fr_t *gamma, const fr_t *theta, const fr_t *y, const fr_t *extended_omega, fr_t *values,
+                         uint32_t log_size, int32_t rot_scale);
+void halo2_prefix_scan(int op, const fr_t *in, uint64_t n, const fr_t *init, fr_t *out);
+int halo2_permutation_product(const fr_t *const *values, const fr_t *const *sigma, uint32_t n_cols, const fr_t *beta,
+                              const fr_t *gamma, const fr_t *delta_omega_start, const fr_t *delta, const fr_t *omega,
+                              uint32_t k, const fr_t *z_init, fr_t *z_out);
+int halo2_logup_running_sum(const fr_t *const *inputs, uint32_t n_inputs, const fr_t *table, const fr_t *m,
+                            const fr_t *beta, uint32_t k, const fr_t *phi_init, fr_t *phi_out);
+
 /* ---- deterministic test-vector generator shared with the GPU tests (xorshift64*) ---- */
 void oracle_fill_fr(fr_t *out, uint64_t n, uint64_t seed, int witness_like);
 void oracle_fill_points(g1_affine_t *out, uint64_t n, uint64_t seed, int threads);

@@ -21,7 +21,8 @@ _SO = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = ["bn254_field.c", "bn254_curve.c", "halo2_arith.c", "halo2_domain.c", "bn254_oracle.h", "fp_template.h"]
+    srcs = ["bn254_field.c", "bn254_curve.c", "halo2_arith.c", "halo2_domain.c", "halo2_quotient.c", "bn254_oracle.h",
+            "fp_template.h"]
     stale = force or not os.path.exists(_SO) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_SO) for s in srcs
     )
@@ -402,4 +403,88 @@ def fill_points_chain(n: int, seed: int, threads: int = 8) -> np.ndarray:
     """distinct valid points P_0 + i*D, cheap to generate at 2^24+ (CPU-baseline inputs only)"""
     out = np.zeros((n, 8), np.uint64)
     lib.oracle_fill_points_chain(_p(out), C.c_uint64(n), C.c_uint64(seed), C.c_int(threads))
+    return out
+
+
+# ---- quotient construction (halo2_quotient.c) ------------------------------------------------------------------
+# program = (calcs, constants, rotations); calcs: list of (op, a, b, parts) with sources (kind, index, rotation)
+SRC = {n: i for i, n in enumerate(["constant", "intermediate", "fixed", "advice", "instance", "challenge", "beta", "gamma",
+                                   "theta", "y", "previous", "x"])}
+CALC = {n: i for i, n in enumerate(["add", "sub", "mul", "square", "double", "negate", "horner", "store"])}
+
+
+class _ValueSource(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32), ("rotation", C.c_uint32)]
+
+
+class _Calculation(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("a", _ValueSource), ("b", _ValueSource), ("parts_offset", C.c_uint32),
+                ("parts_len", C.c_uint32)]
+
+
+def pack_program(calcs, vs_type=_ValueSource, calc_type=_Calculation):
+    parts = []
+    arr = (calc_type * max(1, len(calcs)))()
+    for i, (op, a, b, ps) in enumerate(calcs):
+        arr[i].op = op
+        arr[i].a = vs_type(*a)
+        arr[i].b = vs_type(*(b if b is not None else (0, 0, 0)))
+        arr[i].parts_offset = len(parts)
+        arr[i].parts_len = len(ps or [])
+        parts.extend(ps or [])
+    parr = (vs_type * max(1, len(parts)))(*[vs_type(*q) for q in parts])
+    return arr, parr, len(parts)
+
+
+def _colptrs(cols):
+    cols = [np.ascontiguousarray(c, dtype=np.uint64) for c in cols]
+    arr = (C.c_void_p * max(1, len(cols)))(*[c.ctypes.data for c in cols])
+    return arr, cols
+
+
+def graph_evaluate(calcs, constants, rotations, fixed, advice, instance, challenges, beta, gamma, theta, y,
+                   extended_omega, values, log_size: int, rot_scale: int) -> np.ndarray:
+    arr, parr, _ = pack_program(calcs)
+    consts = np.ascontiguousarray(np.asarray(constants, dtype=np.uint64).reshape(-1, 4))
+    rots = np.ascontiguousarray(np.asarray(rotations, dtype=np.int32))
+    fp, _f = _colptrs(fixed)
+    ap, _a = _colptrs(advice)
+    ip, _i = _colptrs(instance)
+    ch = np.ascontiguousarray(np.asarray(challenges, dtype=np.uint64).reshape(-1, 4))
+    out = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    sc = [np.ascontiguousarray(v, dtype=np.uint64) for v in (beta, gamma, theta, y)]
+    eo = None if extended_omega is None else np.ascontiguousarray(extended_omega, dtype=np.uint64)
+    rc = lib.halo2_graph_evaluate(arr, len(calcs), parr, _p(consts), _p(rots), len(rots), fp, ap, ip, _p(ch), _p(sc[0]),
+                                  _p(sc[1]), _p(sc[2]), _p(sc[3]), None if eo is None else _p(eo), _p(out), log_size,
+                                  rot_scale)
+    assert rc == 0
+    return out
+
+
+def prefix_scan(op: int, a, init) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.zeros_like(a)
+    lib.halo2_prefix_scan(op, _p(a), C.c_uint64(len(a)), _p(np.ascontiguousarray(init, dtype=np.uint64)), _p(out))
+    return out
+
+
+def permutation_product(values, sigma, beta, gamma, delta_omega_start, delta, omega, k: int, z_init) -> np.ndarray:
+    vp, _v = _colptrs(values)
+    sp, _s = _colptrs(sigma)
+    out = np.zeros((1 << k, 4), np.uint64)
+    sc = [np.ascontiguousarray(v, dtype=np.uint64) for v in (beta, gamma, delta_omega_start, delta, omega, z_init)]
+    rc = lib.halo2_permutation_product(vp, sp, len(values), _p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(sc[4]), k,
+                                       _p(sc[5]), _p(out))
+    assert rc == 0
+    return out
+
+
+def logup_running_sum(inputs, table, m, beta, k: int, phi_init) -> np.ndarray:
+    ip, _i = _colptrs(inputs)
+    out = np.zeros((1 << k, 4), np.uint64)
+    t = np.ascontiguousarray(table, dtype=np.uint64)
+    mm = np.ascontiguousarray(m, dtype=np.uint64)
+    sc = [np.ascontiguousarray(v, dtype=np.uint64) for v in (beta, phi_init)]
+    rc = lib.halo2_logup_running_sum(ip, len(inputs), _p(t), _p(mm), _p(sc[0]), k, _p(sc[1]), _p(out))
+    assert rc == 0
     return out

@@ -91,6 +91,14 @@ def _load():
         "b200zk_inner_product": [vp, vp, vp, u64, vp],
         "b200zk_batch_invert": [vp, vp, u64],
         "b200zk_kate_division": [vp, vp, vp, u64, vp],
+        "b200zk_prefix_scan": [vp, C.c_int, vp, u64, vp, vp],
+        "b200zk_permutation_product": [vp, C.POINTER(vp), C.POINTER(vp), u32, vp, vp, vp, vp, vp, u32, vp, vp],
+        "b200zk_logup_running_sum": [vp, C.POINTER(vp), u32, vp, vp, vp, u32, vp, vp],
+        "b200zk_graph_create": [vp, vp, u32, vp, u32, vp, u32, vp, u32, C.POINTER(vp)],
+        "b200zk_graph_destroy": [vp, vp],
+        "b200zk_graph_info": [vp, C.POINTER(u32), C.POINTER(u32)],
+        "b200zk_graph_evaluate": [vp, vp, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp), u32, vp, u32, vp, vp, vp, vp, vp,
+                                  vp, u32, i32],
         "b200zk_debug_field_op": [vp, C.c_int, C.c_int, vp, vp, vp, u64],
         "b200zk_profile_enable": [vp, C.c_int],
         "b200zk_profile_reset": [vp],
@@ -114,7 +122,8 @@ ABI_SYMBOLS = [
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
-    "b200zk_kate_division", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
+    "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create",
+    "b200zk_graph_destroy", "b200zk_graph_info", "b200zk_graph_evaluate", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
 _lib = None
@@ -303,6 +312,47 @@ class Context:
         self._ck(lib().b200zk_ntt_fr_ext(self._h, pi, log_in, po, log_n, pw, int(inverse_scale), coset_mode))
         return out
 
+    # ---- quotient construction (device-resident columns: CUDA tensors)
+    @staticmethod
+    def _dev_table(cols):
+        ptrs = [_ptr(c) for c in cols]
+        return (C.c_void_p * max(1, len(ptrs)))(*[p.value for p, _ in ptrs]), ptrs
+
+    def prefix_scan(self, op: int, a, init, out=None):
+        """out[0] = init, out[i] = out[i-1] (* | +) a[i-1]: the z(X) / phi(X) loops of the permutation / lookup provers."""
+        n = _count(a, 32)
+        out = _like(a) if out is None else out
+        pa, k1 = _ptr(a)
+        pi, k2 = _ptr(init)
+        po, k3 = _ptr(out)
+        self._ck(lib().b200zk_prefix_scan(self._h, op, pa, n, pi, po))
+        return out
+
+    def permutation_product(self, values, sigma, beta, gamma, delta_omega_start, delta, omega, k: int, z_init, out):
+        """permutation::Argument::commit, one column set: z(X) in Lagrange form (blinding rows left to the caller)."""
+        assert len(values) == len(sigma) and _count(out, 32) == 1 << k
+        tv, kv = self._dev_table(values)
+        ts, ks = self._dev_table(sigma)
+        sc = [_ptr(x) for x in (beta, gamma, delta_omega_start, delta, omega)]
+        pz, kz = _ptr(z_init)
+        po, ko = _ptr(out)
+        self._ck(lib().b200zk_permutation_product(self._h, tv, ts, len(values), *[p for p, _ in sc], k, pz, po))
+        return out
+
+    def logup_running_sum(self, inputs, table, m, beta, k: int, phi_init, out):
+        """mv_lookup prover: phi(X) running sum over sum_j 1/(f_j + beta) - m/(t + beta)."""
+        ti, ki = self._dev_table(inputs)
+        pt, k1 = _ptr(table)
+        pm, k2 = _ptr(m)
+        pb, k3 = _ptr(beta)
+        pp, k4 = _ptr(phi_init)
+        po, k5 = _ptr(out)
+        self._ck(lib().b200zk_logup_running_sum(self._h, ti, len(inputs), pt, pm, pb, k, pp, po))
+        return out
+
+    def graph(self, calcs, constants, rotations) -> "Graph":
+        return Graph(self, calcs, constants, rotations)
+
     # ---- poly ops
     def _ew(self, fn, r, *args, n):
         ptrs = [_ptr(x) for x in (r,) + args]
@@ -413,6 +463,80 @@ class Srs:
         if self._h:
             lib().b200zk_srs_release(self.ctx._h, self._h)
             self._h = C.c_void_p()
+
+
+class _ValueSource(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32), ("rotation", C.c_uint32)]
+
+
+class _Calculation(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("a", _ValueSource), ("b", _ValueSource), ("parts_offset", C.c_uint32), ("parts_len", C.c_uint32)]
+
+
+# ValueSource kinds / Calculation ops of include/b200zk.h (plonk::evaluation, upstream declaration order)
+SRC_CONSTANT, SRC_INTERMEDIATE, SRC_FIXED, SRC_ADVICE, SRC_INSTANCE, SRC_CHALLENGE, SRC_BETA, SRC_GAMMA, SRC_THETA, SRC_Y, \
+    SRC_PREVIOUS_VALUE, SRC_EXTENDED_X = range(12)
+CALC_ADD, CALC_SUB, CALC_MUL, CALC_SQUARE, CALC_DOUBLE, CALC_NEGATE, CALC_HORNER, CALC_STORE = range(8)
+SCAN_PRODUCT, SCAN_SUM = 0, 1
+
+
+class Graph:
+    """plonk::evaluation::GraphEvaluator on the device (b200zk_graph).
+
+    calcs: list of (op, a, b, parts); a / b / parts entries are ValueSources (kind, index, rotation_index); b is None
+    for unary calculations, parts is a list only for CALC_HORNER (a = start value, b = factor)."""
+
+    def __init__(self, ctx: Context, calcs, constants, rotations):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        parts = []
+        arr = (_Calculation * max(1, len(calcs)))()
+        for i, (op, a, b, ps) in enumerate(calcs):
+            arr[i].op = op
+            arr[i].a = _ValueSource(*a)
+            arr[i].b = _ValueSource(*(b if b is not None else (0, 0, 0)))
+            arr[i].parts_offset = len(parts)
+            arr[i].parts_len = len(ps or [])
+            parts.extend(ps or [])
+        parr = (_ValueSource * max(1, len(parts)))(*[_ValueSource(*q) for q in parts])
+        consts = np.ascontiguousarray(np.asarray(constants, dtype=np.uint64).reshape(-1, 4))
+        rots = np.ascontiguousarray(np.asarray(rotations, dtype=np.int32).reshape(-1))
+        ctx._ck(lib().b200zk_graph_create(ctx._h, C.cast(arr, C.c_void_p), len(calcs), C.cast(parr, C.c_void_p), len(parts),
+                                          C.c_void_p(consts.ctypes.data), len(consts), C.c_void_p(rots.ctypes.data), len(rots),
+                                          C.byref(self._h)))
+
+    def info(self):
+        ni, ns = C.c_uint32(), C.c_uint32()
+        lib().b200zk_graph_info(self._h, C.byref(ni), C.byref(ns))
+        return {"n_instructions": ni.value, "n_slots": ns.value}
+
+    def evaluate(self, values, log_size: int, rot_scale: int, fixed=(), advice=(), instance=(), challenges=None, beta=None,
+                 gamma=None, theta=None, y=None, extended_omega=None):
+        """values[row] = GraphEvaluator::evaluate(.., previous_value = values[row], ..) for every row of the extended domain."""
+        assert _count(values, 32) == 1 << log_size
+        zero = np.zeros(4, np.uint64)
+        tf, kf = Context._dev_table(fixed)
+        ta, ka = Context._dev_table(advice)
+        ti, ki = Context._dev_table(instance)
+        ch = np.ascontiguousarray(np.asarray(challenges if challenges is not None else [], dtype=np.uint64).reshape(-1, 4))
+        sc = [_ptr(zero if v is None else v) for v in (beta, gamma, theta, y)]
+        pw, kw = _ptr(extended_omega)
+        pv, kv = _ptr(values)
+        self.ctx._ck(lib().b200zk_graph_evaluate(self.ctx._h, self._h, tf, len(fixed), ta, len(advice), ti, len(instance),
+                                                 C.c_void_p(ch.ctypes.data) if len(ch) else None, len(ch), *[p for p, _ in sc], pw, pv,
+                                                 log_size, rot_scale))
+        return values
+
+    def release(self):
+        if self._h:
+            lib().b200zk_graph_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class _ColumnJob(C.Structure):

@@ -29,29 +29,6 @@ using namespace b200zk;
 #define CHECK_CTX(ctx) \
     if (!(ctx)) return B200ZK_E_INVALID
 
-static int32_t read_fr(b200zk_ctx* ctx, const void* p, Fr* out) {
-    if (!p) return fail(ctx, B200ZK_E_INVALID, "null field element pointer");
-    if (is_device_ptr(p)) {
-        B2_CUDA(ctx, cudaMemcpyAsync(out, p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-        B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        memcpy(out, p, sizeof(Fr));
-    }
-    uint32_t m[8], d[8];
-    Fr::modulus(m);
-    if (!leaf::sub8(d, out->l.v, m)) return fail(ctx, B200ZK_E_INVALID, "field element is not reduced (>= modulus)");
-    return B200ZK_OK;
-}
-
-// result delivery: dev -> (host | device) pointer
-static int32_t deliver(b200zk_ctx* ctx, void* dst, const void* dev_src, size_t bytes) {
-    if (is_device_ptr(dst)) {
-        if (dst != dev_src) B2_CUDA(ctx, cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        return B200ZK_OK;
-    }
-    return d2h(ctx, dst, dev_src, bytes);
-}
-
 extern "C" {
 
 int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out) {

@@ -216,8 +216,33 @@ struct Guard {
     explicit Guard(b200zk_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
 };
 
+// a 32 B field element argument (host or device pointer) -> host value; rejects unreduced limbs
+inline int32_t read_fr(b200zk_ctx* ctx, const void* p, Fr* out) {
+    if (!p) return fail(ctx, B200ZK_E_INVALID, "null field element pointer");
+    if (is_device_ptr(p)) {
+        B2_CUDA(ctx, cudaMemcpyAsync(out, p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(out, p, sizeof(Fr));
+    }
+    uint32_t m[8], d[8];
+    Fr::modulus(m);
+    if (!leaf::sub8(d, out->l.v, m)) return fail(ctx, B200ZK_E_INVALID, "field element is not reduced (>= modulus)");
+    return B200ZK_OK;
+}
+
+// result delivery: dev -> (host | device) pointer
+inline int32_t deliver(b200zk_ctx* ctx, void* dst, const void* dev_src, size_t bytes) {
+    if (is_device_ptr(dst)) {
+        if (dst != dev_src) B2_CUDA(ctx, cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200ZK_OK;
+    }
+    return d2h(ctx, dst, dev_src, bytes);
+}
+
 // implemented in ntt.cu / msm.cu / poly.cu
 int32_t ntt_get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const Fr** out);
+Fr host_zeta();
 int32_t ntt_run(b200zk_ctx* ctx, const Fr* in, uint32_t log_in, Fr* out, uint32_t log_n, const Fr& omega,
                 int inverse_scale, int coset_mode);
 

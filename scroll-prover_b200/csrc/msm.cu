@@ -492,7 +492,7 @@ static uint32_t pick_window(uint64_t n) {
     for (uint32_t c = 5; c <= 23; ++c) {
         uint32_t W = 254 / c + 1;
         if ((double)n * W >= 4.0e9) continue;  // sorted-entry positions are 32-bit
-        double cost = (double)n * W * 10.0 + (double)W * (double)(1ull << c) * 16.0 + (double)W * 4096.0;
+        double cost = (double)n * W * 10.0 + (double)W * (double)(1ull << c) * 40.0 + (double)W * 4096.0;
         if (cost < best) {
             best = cost;
             bc = c;

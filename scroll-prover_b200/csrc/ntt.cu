@@ -289,7 +289,7 @@ static Fr host_halve(const Fr& x) {  // x/2 mod r (linear, so valid on Montgomer
     return r;
 }
 
-static Fr host_zeta() {  // halo2curves Fr::ZETA in Montgomery form
+Fr host_zeta() {  // halo2curves Fr::ZETA in Montgomery form
     Fr z;
     const uint32_t v[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu,
                            0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};

@@ -55,3 +55,80 @@ extern "C" void ec_host_op(int op, uint32_t* out_affine16, const uint32_t* acc_j
     a.y = r.z.is_zero() ? Fq::zero() : r.y;
     memcpy(out_affine16, &a, 64);
 }
+
+// ---- graph.hpp + graph_exec.cuh under host emulation: the product's program lowering and row interpreter run on
+// the CPU with plain-array slots (tests/test_graph_host_emul.py); only the CUDA kernel wrapper is not exercised here.
+#include "../../scroll-prover_b200/csrc/graph_exec.cuh"
+#include <vector>
+namespace {
+struct ArrSlots {
+    std::vector<Fr>* v;
+    Fr load(uint32_t s) const { return (*v)[s]; }
+    void store(uint32_t s, const Fr& x) { (*v)[s] = x; }
+};
+struct ArrCols {
+    const Fr* const* cols;
+    const uint32_t* rot_off;
+    uint64_t row, mask;
+    Fr load(uint32_t col, uint32_t rot) const { return cols[col][(row + rot_off[rot]) & mask]; }
+};
+struct ArrConsts {
+    const Fr* c;
+    Fr load(uint32_t i) const { return c[i]; }
+};
+}  // namespace
+// returns 0 and fills info[0] = instructions, info[1] = slots; or -1 with the compile error in err (<= 255 chars)
+extern "C" int graph_host_eval(const b200zk_calculation* calcs, uint32_t n_calcs, const b200zk_value_source* parts, uint32_t n_parts,
+                               const uint32_t* constants, uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations,
+                               const void* const* fixed, uint32_t n_fixed, const void* const* advice, uint32_t n_advice,
+                               const void* const* instance, uint32_t n_instance, const uint32_t* challenges, uint32_t n_challenges,
+                               const uint32_t* bgty /* beta gamma theta y */, const uint32_t* ext_omega, uint32_t* values,
+                               uint32_t log_size, int32_t rot_scale, uint32_t* info, char* err) {
+    GraphProgram P;
+    std::string e = graph_compile(calcs, n_calcs, parts, n_parts, n_constants, n_rotations, &P);
+    if (e.empty() && (P.need_cols[0] > n_fixed || P.need_cols[1] > n_advice || P.need_cols[2] > n_instance ||
+                      P.need_challenges > n_challenges))
+        e = "not enough columns / challenges";
+    if (!e.empty()) {
+        snprintf(err, 256, "%s", e.c_str());
+        return -1;
+    }
+    info[0] = (uint32_t)P.instrs.size();
+    info[1] = P.n_slots;
+    std::vector<Fr> consts(n_constants + 4 + P.need_challenges);
+    if (n_constants) memcpy(consts.data(), constants, 32 * (size_t)n_constants);
+    memcpy(&consts[n_constants], bgty, 128);
+    if (P.need_challenges) memcpy(&consts[n_constants + 4], challenges, 32 * (size_t)P.need_challenges);
+    std::vector<const Fr*> cols;
+    for (uint32_t i = 0; i < P.need_cols[0]; ++i) cols.push_back((const Fr*)fixed[i]);
+    for (uint32_t i = 0; i < P.need_cols[1]; ++i) cols.push_back((const Fr*)advice[i]);
+    for (uint32_t i = 0; i < P.need_cols[2]; ++i) cols.push_back((const Fr*)instance[i]);
+    cols.push_back(nullptr);
+    const uint64_t size = 1ull << log_size;
+    std::vector<uint32_t> rot_off(n_rotations + 1);
+    for (uint32_t r = 0; r < n_rotations; ++r) {
+        int64_t v = ((int64_t)rotations[r] * rot_scale) % (int64_t)size;
+        if (v < 0) v += (int64_t)size;
+        rot_off[r] = (uint32_t)v;
+    }
+    Fr zeta, w = Fr::one(), x;
+    {   // Fr::ZETA (same constant as ntt.cu's host_zeta)
+        const uint32_t v[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu, 0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+        memcpy(zeta.l.v, v, 32);
+    }
+    Fr om = Fr::one();
+    if (ext_omega) memcpy(om.l.v, ext_omega, 32);
+    std::vector<Fr> slots(P.n_slots);
+    Fr* vals = (Fr*)values;
+    for (uint64_t row = 0; row < size; ++row) {
+        ArrSlots S{&slots};
+        if (P.uses_prev) S.store(G_SLOT_PREV, vals[row]);
+        if (P.uses_x) S.store(G_SLOT_X, zeta * w);
+        ArrCols Cc{cols.data(), rot_off.data(), row, size - 1};
+        ArrConsts K{consts.data()};
+        graph_exec_row(P.instrs.data(), (uint32_t)P.instrs.size(), S, Cc, K);
+        vals[row] = (P.out_slot == G_NO_RESULT) ? Fr::zero() : S.load(P.out_slot);
+        w = w * om;
+    }
+    return 0;
+}
