@@ -16,6 +16,21 @@ from quotient_programs import (C_HORNER, C_MUL, C_STORE, C_SUB, DELTA, R_MOD, S_
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def one_stream(ctx):
+    """The ABI is asynchronous on the context stream for device-resident outputs.  These tests hand torch tensors in and
+    read torch tensors back, so the library is put on torch's current (non-default) stream for their duration: clones,
+    kernels and .cpu() copies are then ordered on one stream, as a device-resident prover session would run them."""
+    import torch
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ctx.set_stream(s.cuda_stream)
+        yield
+        ctx.synchronize()
+    ctx.set_stream(None)
+
+
 def dev(a):
     import torch
 
