@@ -3,8 +3,10 @@
 //
 // Upstream (halo2_proofs/src/plonk/evaluation.rs @ e5ddf67, pin /root/reference/Cargo.lock:1886-1888) keeps one
 // intermediate per calculation in a Vec<F> per thread.  On the device the live values of a row sit in shared memory,
-// so the program is lowered first: dead calculations are dropped, every surviving one gets an on-chip slot by a
-// linear scan over last uses, Horner becomes MOV + a run of MADs, and every ValueSource becomes one operand word.
+// so the program is lowered first: dead calculations are dropped; the rest is re-emitted demand-driven from the result
+// (a value is computed right before its first reader, so `value = value * y + gate_i` chains keep ONE gate value live,
+// not all of them); slots are recycled by outstanding-use counts; Horner becomes (MOV +) a run of MADs; every
+// ValueSource becomes one operand word.  Fewer live slots = more rows resident per SM.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -100,23 +102,39 @@ inline std::string graph_compile(const b200zk_calculation* calcs, uint32_t n_cal
         }
     }
     if (n_calcs == 0) return "";
-    // liveness: only what the last calculation (the result) depends on is evaluated
+    // liveness: only what the last calculation (the result) depends on is evaluated; uses[j] counts the operand
+    // occurrences that still have to read intermediate j
     std::vector<char> needed(n_calcs, 0);
-    std::vector<uint32_t> last_use(n_calcs, 0);
+    std::vector<uint32_t> uses(n_calcs, 0);
     needed[n_calcs - 1] = 1;
-    last_use[n_calcs - 1] = n_calcs;  // the result outlives the program
     for (uint32_t i = n_calcs; i-- > 0;) {
         if (!needed[i]) continue;
         for (const auto& s : src[i])
             if (s.kind == B200ZK_SRC_INTERMEDIATE) {
-                if (!needed[s.index]) {
-                    needed[s.index] = 1;
-                    last_use[s.index] = i;  // i descends: the first visit is the last use
-                }
+                needed[s.index] = 1;
+                uses[s.index]++;
             }
     }
+    uses[n_calcs - 1]++;  // the result outlives the program
     std::vector<uint32_t> slot_of(n_calcs, 0), free_slots;
+    std::vector<char> done(n_calcs, 0);
     uint32_t next_slot = G_SLOT_FIRST;
+    bool overflow = false;
+    auto alloc = [&]() -> uint32_t {
+        if (!free_slots.empty()) {
+            uint32_t s = free_slots.back();
+            free_slots.pop_back();
+            return s;
+        }
+        if (next_slot >= G_MAX_SLOTS) {
+            overflow = true;
+            return G_MAX_SLOTS - 1;
+        }
+        return next_slot++;
+    };
+    auto consume = [&](const b200zk_value_source& s) {  // one operand occurrence has been read
+        if (s.kind == B200ZK_SRC_INTERMEDIATE && --uses[s.index] == 0) free_slots.push_back(slot_of[s.index]);
+    };
     auto encode = [&](const b200zk_value_source& s) -> uint32_t {
         switch (s.kind) {
             case B200ZK_SRC_CONSTANT: return g_operand(GK_CONST, s.index);
@@ -137,39 +155,76 @@ inline std::string graph_compile(const b200zk_calculation* calcs, uint32_t n_cal
             default: P.uses_x = true; return g_operand(GK_SLOT, G_SLOT_X);
         }
     };
-    for (uint32_t i = 0; i < n_calcs; ++i) {
-        if (!needed[i]) continue;
+    auto emit = [&](uint32_t op, uint32_t dst, uint32_t a, uint32_t b) { P.instrs.push_back(GInstr{op | (dst << 8), a, b, 0}); };
+    // Demand-driven emission from the result (explicit stack: programs can be deep): an intermediate is computed right
+    // before its first reader, so a Horner over many gate values keeps one of them live at a time instead of all.
+    // A frame walks the operands of one calculation; `cur` is the next operand to make available, and for a Horner
+    // the MOV / MADs are emitted as the walk passes the start value / each part.
+    struct Frame {
+        uint32_t i, cur, dst;
+    };
+    std::vector<Frame> stack;
+    stack.push_back(Frame{n_calcs - 1, 0, 0});
+    while (!stack.empty()) {
+        Frame& f = stack.back();
+        const uint32_t i = f.i;
         const b200zk_calculation& c = calcs[i];
-        // the destination is taken before the operands are released: a MAD run rewrites dst while its parts are live
-        uint32_t dst;
-        if (!free_slots.empty()) {
-            dst = free_slots.back();
-            free_slots.pop_back();
+        const auto& sv = src[i];
+        const bool horner = c.op == B200ZK_CALC_HORNER;
+        bool descended = false;
+        while (f.cur < sv.size()) {
+            const b200zk_value_source& s = sv[f.cur];
+            if (s.kind == B200ZK_SRC_INTERMEDIATE && !done[s.index]) {
+                stack.push_back(Frame{s.index, 0, 0});  // invalidates f
+                descended = true;
+                break;
+            }
+            if (horner) {
+                // sv = [start, factor, parts...]: the factor must be ready before the first MAD, so operand 1 is only
+                // waited for here; emission happens when the walk passes operand 0 (after 1 is ready) and each part
+                if (f.cur == 1) {
+                    // start and factor are both available: open the accumulator.  It may take over the start value's
+                    // slot when this is that value's last reader (no MOV); otherwise a fresh slot -- never one that a
+                    // pending part or the factor still occupies, because those still have a use outstanding.
+                    if (c.a.kind == B200ZK_SRC_INTERMEDIATE && uses[c.a.index] == 1) {
+                        f.dst = slot_of[c.a.index];
+                        uses[c.a.index] = 0;
+                    } else {
+                        uint32_t a = encode(c.a);
+                        f.dst = alloc();
+                        emit(GI_MOV, f.dst, a, 0);
+                        consume(c.a);
+                    }
+                } else if (f.cur >= 2) {
+                    emit(GI_MAD, f.dst, encode(s), encode(c.b));
+                    consume(s);
+                }
+            }
+            f.cur++;
+        }
+        if (descended) continue;
+        if (horner) {
+            consume(c.b);
         } else {
-            dst = next_slot++;
-            if (next_slot > G_MAX_SLOTS) return "program keeps too many intermediates live at once (split it with PreviousValue)";
-        }
-        slot_of[i] = dst;
-        auto emit = [&](uint32_t op, uint32_t a, uint32_t b) { P.instrs.push_back(GInstr{op | (dst << 8), a, b, 0}); };
-        switch (c.op) {
-            case B200ZK_CALC_ADD: emit(GI_ADD, encode(c.a), encode(c.b)); break;
-            case B200ZK_CALC_SUB: emit(GI_SUB, encode(c.a), encode(c.b)); break;
-            case B200ZK_CALC_MUL: emit(GI_MUL, encode(c.a), encode(c.b)); break;
-            case B200ZK_CALC_SQUARE: emit(GI_SQR, encode(c.a), 0); break;
-            case B200ZK_CALC_DOUBLE: emit(GI_DBL, encode(c.a), 0); break;
-            case B200ZK_CALC_NEGATE: emit(GI_NEG, encode(c.a), 0); break;
-            case B200ZK_CALC_STORE: emit(GI_MOV, encode(c.a), 0); break;
-            default: {  // Horner(start, parts, factor): value = start; for part: value = value * factor + part
-                emit(GI_MOV, encode(c.a), 0);
-                uint32_t f = encode(c.b);
-                for (uint32_t j = 0; j < c.parts_len; ++j) emit(GI_MAD, encode(parts[c.parts_offset + j]), f);
+            // operands are read before the destination is written, so the destination may reuse an operand's slot
+            uint32_t a = encode(c.a), b = (sv.size() > 1) ? encode(c.b) : 0;
+            consume(c.a);
+            if (sv.size() > 1) consume(c.b);
+            f.dst = alloc();
+            switch (c.op) {
+                case B200ZK_CALC_ADD: emit(GI_ADD, f.dst, a, b); break;
+                case B200ZK_CALC_SUB: emit(GI_SUB, f.dst, a, b); break;
+                case B200ZK_CALC_MUL: emit(GI_MUL, f.dst, a, b); break;
+                case B200ZK_CALC_SQUARE: emit(GI_SQR, f.dst, a, 0); break;
+                case B200ZK_CALC_DOUBLE: emit(GI_DBL, f.dst, a, 0); break;
+                case B200ZK_CALC_NEGATE: emit(GI_NEG, f.dst, a, 0); break;
+                default: emit(GI_MOV, f.dst, a, 0); break;
             }
         }
-        for (const auto& s : src[i])
-            if (s.kind == B200ZK_SRC_INTERMEDIATE && last_use[s.index] == i) {
-                free_slots.push_back(slot_of[s.index]);
-                last_use[s.index] = 0xffffffffu;  // release once even when named twice
-            }
+        slot_of[i] = f.dst;
+        done[i] = 1;
+        stack.pop_back();
+        if (overflow) return "program keeps too many intermediates live at once (split it with PreviousValue)";
     }
     P.n_slots = next_slot;
     P.out_slot = slot_of[n_calcs - 1];

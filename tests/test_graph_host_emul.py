@@ -136,9 +136,42 @@ def test_malformed_programs_are_rejected(lib, calcs, msg):
     assert rc == -1 and msg in err
 
 
+def test_very_deep_dependency_chain(lib):
+    # 60 000 calculations, each reading the previous one: the lowering walks it with an explicit stack
+    calcs = [(C_STORE, (S_ADVICE, 0, 0), None, None)]
+    for i in range(60000):
+        calcs.append((C_MUL if i % 2 else C_ADD, (S_INTER, i, 0), (S_ADVICE, 0, 0), None))
+    ad = [O.fill_fr(2, 5)]
+    z = O.fr_from_int(0)
+    e = np.zeros((0, 4), np.uint64)
+    want = O.graph_evaluate(calcs, e, [0], [], ad, [], e, z, z, z, z, None, np.zeros((2, 4), np.uint64), 1, 1)
+    rc, got, (n_instr, n_slots), err = host_eval(lib, calcs, e, [0], [], ad, [], e, [z, z, z, z], None, np.zeros((2, 4), np.uint64), 1, 1)
+    assert rc == 0, err
+    assert np.array_equal(got, want) and n_instr == 60001 and n_slots == 3
+
+
+def test_values_are_computed_right_before_their_first_reader(lib):
+    # 300 gate values folded by one Horner: demand-driven emission keeps one of them live at a time
+    calcs = [(C_MUL, (S_ADVICE, 0, 0), (S_ADVICE, 0, 1), None) for _ in range(300)]
+    calcs.append((C_HORNER, (S_PREV, 0, 0), (S_CONST, 0, 0), [(S_INTER, i, 0) for i in range(300)]))
+    ad = [O.fill_fr(8, 5)]
+    consts = O.frs_from_ints([77])
+    z = O.fr_from_int(0)
+    e = np.zeros((0, 4), np.uint64)
+    prev = O.fill_fr(8, 6)
+    want = O.graph_evaluate(calcs, consts, [0, 1], [], ad, [], e, z, z, z, z, None, prev, 3, 1)
+    rc, got, (n_instr, n_slots), err = host_eval(lib, calcs, consts, [0, 1], [], ad, [], e, [z, z, z, z], None, prev, 3, 1)
+    assert rc == 0, err
+    assert np.array_equal(got, want)
+    assert n_slots <= 2 + 2 and n_instr == 300 + 1 + 300  # 300 MUL, MOV, 300 MAD
+
+
 def test_too_many_live_intermediates_is_reported(lib):
+    # 300 values, each read by two Horner runs in opposite orders: all of them are live when the first run ends
     calcs = [(C_STORE, (S_ADVICE, 0, 0), None, None) for _ in range(300)]
     calcs.append((C_HORNER, (S_CONST, 0, 0), (S_CONST, 0, 0), [(S_INTER, i, 0) for i in range(300)]))
+    calcs.append((C_HORNER, (S_CONST, 0, 0), (S_CONST, 0, 0), [(S_INTER, 299 - i, 0) for i in range(300)]))
+    calcs.append((C_ADD, (S_INTER, 300, 0), (S_INTER, 301, 0), None))
     z = O.fr_from_int(0)
     e = np.zeros((0, 4), np.uint64)
     rc, _, _, err = host_eval(lib, calcs, O.frs_from_ints([1]), [0], [], [O.fill_fr(2, 1)], [], e, [z, z, z, z], None,
