@@ -312,4 +312,164 @@ inline std::vector<G1> commit_columns(ParamsKZG& params, const EvaluationDomain&
     return out;
 }
 
+// A column (Polynomial<Fr, _>) resident on the device between calls: b200zk_buf_alloc / upload / download.
+class DeviceColumn {
+  public:
+    DeviceColumn() = default;
+    explicit DeviceColumn(size_t len) : len_(len) {
+        auto& b = Backend::get();
+        b.check(b200zk_buf_alloc(b.ctx(), 32 * (uint64_t)len, &dev_), "DeviceColumn::alloc");
+    }
+    explicit DeviceColumn(const std::vector<Fr>& host) : DeviceColumn(host.size()) { upload(host); }
+    DeviceColumn(const DeviceColumn&) = delete;
+    DeviceColumn& operator=(const DeviceColumn&) = delete;
+    DeviceColumn(DeviceColumn&& o) noexcept : dev_(o.dev_), len_(o.len_) { o.dev_ = nullptr; }
+    ~DeviceColumn() {
+        if (dev_) b200zk_buf_free(Backend::get().ctx(), dev_);
+    }
+    void upload(const std::vector<Fr>& host) {
+        if (host.size() != len_) throw Panic("DeviceColumn::upload: length mismatch");
+        auto& b = Backend::get();
+        b.check(b200zk_buf_upload(b.ctx(), dev_, host.data(), 32 * (uint64_t)len_), "DeviceColumn::upload");
+    }
+    std::vector<Fr> to_host() const {
+        std::vector<Fr> out(len_);
+        auto& b = Backend::get();
+        b.check(b200zk_buf_download(b.ctx(), out.data(), dev_, 32 * (uint64_t)len_), "DeviceColumn::download");
+        return out;
+    }
+    void* ptr() const { return dev_; }
+    size_t len() const { return len_; }
+
+  private:
+    void* dev_ = nullptr;
+    size_t len_ = 0;
+};
+
+// halo2_proofs::plonk -- the prover steps between the transforms, on device-resident columns
+namespace plonk {
+
+// plonk::evaluation::ValueSource / Calculation / GraphEvaluator (evaluation.rs): same construction interface --
+// add_constant / add_rotation / add_calculation return the index a later ValueSource names.
+struct ValueSource {
+    uint32_t kind, index, rotation;
+    static ValueSource Constant(uint32_t i) { return {B200ZK_SRC_CONSTANT, i, 0}; }
+    static ValueSource Intermediate(uint32_t i) { return {B200ZK_SRC_INTERMEDIATE, i, 0}; }
+    static ValueSource Fixed(uint32_t col, uint32_t rot) { return {B200ZK_SRC_FIXED, col, rot}; }
+    static ValueSource Advice(uint32_t col, uint32_t rot) { return {B200ZK_SRC_ADVICE, col, rot}; }
+    static ValueSource Instance(uint32_t col, uint32_t rot) { return {B200ZK_SRC_INSTANCE, col, rot}; }
+    static ValueSource Challenge(uint32_t i) { return {B200ZK_SRC_CHALLENGE, i, 0}; }
+    static ValueSource Beta() { return {B200ZK_SRC_BETA, 0, 0}; }
+    static ValueSource Gamma() { return {B200ZK_SRC_GAMMA, 0, 0}; }
+    static ValueSource Theta() { return {B200ZK_SRC_THETA, 0, 0}; }
+    static ValueSource Y() { return {B200ZK_SRC_Y, 0, 0}; }
+    static ValueSource PreviousValue() { return {B200ZK_SRC_PREVIOUS_VALUE, 0, 0}; }
+    static ValueSource ExtendedX() { return {B200ZK_SRC_EXTENDED_X, 0, 0}; }  // not upstream: the coset point of the row
+};
+
+class GraphEvaluator {
+  public:
+    GraphEvaluator() {  // upstream seeds the constants with 0, 1, 2
+        add_constant(detail::from_dev(detail::DFr::zero()));
+        add_constant(detail::from_dev(detail::DFr::one()));
+        add_constant(detail::from_dev(detail::DFr::one() + detail::DFr::one()));
+    }
+    GraphEvaluator(const GraphEvaluator&) = delete;
+    GraphEvaluator& operator=(const GraphEvaluator&) = delete;
+    ~GraphEvaluator() { release(); }
+
+    uint32_t add_rotation(int32_t rotation) {
+        for (size_t i = 0; i < rotations_.size(); ++i)
+            if (rotations_[i] == rotation) return (uint32_t)i;
+        rotations_.push_back(rotation);
+        dirty();
+        return (uint32_t)rotations_.size() - 1;
+    }
+    ValueSource add_constant(const Fr& c) {
+        for (size_t i = 0; i < constants_.size(); ++i)
+            if (constants_[i] == c) return ValueSource::Constant((uint32_t)i);
+        constants_.push_back(c);
+        dirty();
+        return ValueSource::Constant((uint32_t)constants_.size() - 1);
+    }
+    ValueSource add(uint32_t op, ValueSource a, ValueSource b = ValueSource::Constant(0)) {
+        calcs_.push_back(b200zk_calculation{op, {a.kind, a.index, a.rotation}, {b.kind, b.index, b.rotation}, 0, 0});
+        dirty();
+        return ValueSource::Intermediate((uint32_t)calcs_.size() - 1);
+    }
+    // Calculation::Horner(start_value, parts, factor)
+    ValueSource add_horner(ValueSource start, const std::vector<ValueSource>& parts, ValueSource factor) {
+        b200zk_calculation c{B200ZK_CALC_HORNER, {start.kind, start.index, start.rotation}, {factor.kind, factor.index, factor.rotation},
+                             (uint32_t)parts_.size(), (uint32_t)parts.size()};
+        for (const auto& p : parts) parts_.push_back(b200zk_value_source{p.kind, p.index, p.rotation});
+        calcs_.push_back(c);
+        dirty();
+        return ValueSource::Intermediate((uint32_t)calcs_.size() - 1);
+    }
+    size_t num_calculations() const { return calcs_.size(); }
+
+    // GraphEvaluator::evaluate for every row of the extended domain: values[row] = f(previous = values[row], row)
+    void evaluate(DeviceColumn& values, const EvaluationDomain& dom, const std::vector<const DeviceColumn*>& fixed,
+                  const std::vector<const DeviceColumn*>& advice, const std::vector<const DeviceColumn*>& instance,
+                  const std::vector<Fr>& challenges, const Fr& beta, const Fr& gamma, const Fr& theta, const Fr& y) {
+        auto& b = Backend::get();
+        if (values.len() != (size_t(1) << dom.extended_k)) throw Panic("GraphEvaluator::evaluate: values must cover the extended domain");
+        if (!graph_)
+            b.check(b200zk_graph_create(b.ctx(), calcs_.data(), (uint32_t)calcs_.size(), parts_.data(), (uint32_t)parts_.size(),
+                                        constants_.data(), (uint32_t)constants_.size(), rotations_.data(), (uint32_t)rotations_.size(),
+                                        &graph_),
+                    "GraphEvaluator::compile");
+        auto table = [](const std::vector<const DeviceColumn*>& v) {
+            std::vector<const void*> t;
+            for (auto* c : v) t.push_back(c->ptr());
+            return t;
+        };
+        auto tf = table(fixed), ta = table(advice), ti = table(instance);
+        const int32_t rot_scale = 1 << (dom.extended_k - dom.k);
+        b.check(b200zk_graph_evaluate(b.ctx(), graph_, tf.data(), (uint32_t)tf.size(), ta.data(), (uint32_t)ta.size(), ti.data(),
+                                      (uint32_t)ti.size(), challenges.data(), (uint32_t)challenges.size(), &beta, &gamma, &theta, &y,
+                                      &dom.extended_omega, values.ptr(), dom.extended_k, rot_scale),
+                "GraphEvaluator::evaluate");
+    }
+    void release() {
+        if (graph_) b200zk_graph_destroy(Backend::get().ctx(), graph_);
+        graph_ = nullptr;
+    }
+
+  private:
+    void dirty() { release(); }
+    std::vector<b200zk_calculation> calcs_;
+    std::vector<b200zk_value_source> parts_;
+    std::vector<Fr> constants_;
+    std::vector<int32_t> rotations_;
+    b200zk_graph* graph_ = nullptr;
+};
+
+// permutation::Argument::commit, one column set: z in Lagrange form (the caller applies the blinding rows and chains
+// z[n - (blinding_factors + 1)] into the next set as z_init, as upstream does)
+inline void permutation_product(const std::vector<const DeviceColumn*>& values, const std::vector<const DeviceColumn*>& sigma,
+                                const Fr& beta, const Fr& gamma, const Fr& delta_omega_start, const Fr& delta,
+                                const EvaluationDomain& dom, const Fr& z_init, DeviceColumn& z_out) {
+    if (values.size() != sigma.size()) throw Panic("permutation_product: columns.len() != permutations.len()");
+    std::vector<const void*> tv, ts;
+    for (auto* c : values) tv.push_back(c->ptr());
+    for (auto* c : sigma) ts.push_back(c->ptr());
+    auto& b = Backend::get();
+    b.check(b200zk_permutation_product(b.ctx(), tv.data(), ts.data(), (uint32_t)tv.size(), &beta, &gamma, &delta_omega_start, &delta,
+                                       &dom.omega, dom.k, &z_init, z_out.ptr()),
+            "permutation_product");
+}
+
+// mv_lookup prover: the phi(X) running sum
+inline void logup_running_sum(const std::vector<const DeviceColumn*>& inputs, const DeviceColumn& table, const DeviceColumn& m,
+                              const Fr& beta, const EvaluationDomain& dom, const Fr& phi_init, DeviceColumn& phi_out) {
+    std::vector<const void*> ti;
+    for (auto* c : inputs) ti.push_back(c->ptr());
+    auto& b = Backend::get();
+    b.check(b200zk_logup_running_sum(b.ctx(), ti.data(), (uint32_t)ti.size(), table.ptr(), m.ptr(), &beta, dom.k, &phi_init, phi_out.ptr()),
+            "logup_running_sum");
+}
+
+}  // namespace plonk
+
 }  // namespace halo2_b200
