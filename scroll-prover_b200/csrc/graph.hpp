@@ -25,7 +25,7 @@ enum { GK_CONST = 0, GK_SLOT = 1, GK_COL = 2 };
 //   GK_SLOT  payload: slot (0 = PreviousValue, 1 = extended X, >= 2 intermediates)
 //   GK_COL   payload: rotation index << 16 | position in the call's column table, which lists the columns the program
 //            reads as fixed[0..need_cols[0]) | advice[0..need_cols[1]) | instance[0..need_cols[2])
-struct GInstr {
+struct alignas(16) GInstr {  // one 128-bit load per instruction
     uint32_t op_dst;  // op | dst slot << 8
     uint32_t a, b, pad;
 };

@@ -122,8 +122,11 @@ static uint32_t graph_block_rows(uint32_t n_slots, size_t* smem_bytes) {
     for (uint32_t t = 128; t >= 32; t >>= 1) {
         size_t per_block = (size_t)n_slots * 32 * t;
         if (per_block > budget) continue;
-        size_t rows = (budget / per_block) * t;
-        if (rows > best_rows) {
+        size_t blocks = budget / (per_block + 1024);  // + the per-block shared-memory reservation of the driver
+        if (blocks > 32) blocks = 32;                 // resident-block limit of an SM
+        size_t rows = blocks * t;
+        if (rows > 1280) rows = 1280;                 // ~52 registers per thread: 64 K registers hold ~1260 rows
+        if (rows > best_rows) {                       // ties go to the wider block (fewer blocks to schedule)
             best_rows = rows;
             best_t = t;
         }
