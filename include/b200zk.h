@@ -178,6 +178,11 @@ B200ZK_API int32_t b200zk_kate_division(b200zk_ctx* ctx, void* q, const void* a,
 #define B200ZK_SCAN_SUM 1
 B200ZK_API int32_t b200zk_prefix_scan(b200zk_ctx* ctx, int op, const void* in_dev, uint64_t n, const void* init32, void* out_dev);
 
+/* out[i] = sum_j scalars[j] * polys[j][i], i < n: one pass over the inputs (the SHPLONK prover's per-rotation-set
+ * sum_i v^i p_i(X) and its final linear combination; poly/kzg/multiopen/shplonk/prover.rs).  out may alias one input. */
+B200ZK_API int32_t b200zk_poly_lincomb(b200zk_ctx* ctx, void* out_dev, const void* const* polys_dev, const void* scalars32,
+                                       uint32_t count, uint64_t n);
+
 /* One column set of the permutation argument (permutation::Argument::commit, one iteration of its chunk loop):
  *   mv[i]  = prod_j (beta * sigma_j[i] + gamma + v_j[i])            (denominators, then ff::BatchInvert)
  *   mv[i] *= prod_j (delta_omega_j * omega^i * beta + gamma + v_j[i]),  delta_omega_j = delta_omega_start * delta^j

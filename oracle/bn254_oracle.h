@@ -130,6 +130,15 @@ int halo2_permutation_product(const fr_t *const *values, const fr_t *const *sigm
 int halo2_logup_running_sum(const fr_t *const *inputs, uint32_t n_inputs, const fr_t *table, const fr_t *m,
                             const fr_t *beta, uint32_t k, const fr_t *phi_init, fr_t *phi_out);
 
+int halo2_permutation_h_terms(const fr_t *const *z_cosets, uint32_t n_sets, uint32_t chunk_len, const fr_t *const *value_cosets,
+                              const fr_t *const *sigma_cosets, uint32_t n_cols, const fr_t *l0, const fr_t *l_last,
+                              const fr_t *l_active_row, const fr_t *beta, const fr_t *gamma, const fr_t *y, const fr_t *delta,
+                              const fr_t *extended_omega, int32_t last_rotation, fr_t *values, uint32_t log_size,
+                              int32_t rot_scale);
+int halo2_logup_h_terms(const fr_t *const *input_cosets, uint32_t n_inputs, const fr_t *table_coset, const fr_t *m_coset,
+                        const fr_t *phi_coset, const fr_t *l0, const fr_t *l_last, const fr_t *l_active_row, const fr_t *beta,
+                        const fr_t *y, fr_t *values, uint32_t log_size, int32_t rot_scale);
+
 /* ---- deterministic test-vector generator shared with the GPU tests (xorshift64*) ---- */
 void oracle_fill_fr(fr_t *out, uint64_t n, uint64_t seed, int witness_like);
 void oracle_fill_points(g1_affine_t *out, uint64_t n, uint64_t seed, int threads);

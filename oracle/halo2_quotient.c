@@ -172,3 +172,116 @@ int halo2_logup_running_sum(const fr_t *const *inputs, uint32_t n_inputs, const 
     free(d);
     return 0;
 }
+
+/* ---- evaluate_h, the permutation section (plonk/evaluation.rs, `// Permutations`), for all rows of the extended domain:
+ *   value = value*y + (1 - z_0[idx]) * l0[idx]
+ *   value = value*y + (z_last[idx]^2 - z_last[idx]) * l_last[idx]
+ *   for sets i >= 1:  value = value*y + (z_i[idx] - z_{i-1}[r_last]) * l0[idx]
+ *   for every set (columns in chunks of chunk_len):
+ *       left  = z_i[r_next] * prod_j (v_j[idx] + beta*sigma_j[idx] + gamma)
+ *       right = z_i[idx]    * prod_j (v_j[idx] + current_delta + gamma),  current_delta *= DELTA after each column
+ *       value = value*y + (left - right) * l_active_row[idx]
+ * with current_delta starting at beta * ZETA * extended_omega^idx for the first column of the first set,
+ * r_next = (idx + rot_scale) mod isize, r_last = (idx + last_rotation*rot_scale) mod isize. */
+int halo2_permutation_h_terms(const fr_t *const *z_cosets, uint32_t n_sets, uint32_t chunk_len, const fr_t *const *value_cosets,
+                              const fr_t *const *sigma_cosets, uint32_t n_cols, const fr_t *l0, const fr_t *l_last,
+                              const fr_t *l_active_row, const fr_t *beta, const fr_t *gamma, const fr_t *y, const fr_t *delta,
+                              const fr_t *extended_omega, int32_t last_rotation, fr_t *values, uint32_t log_size,
+                              int32_t rot_scale) {
+    const int64_t isize = (int64_t)1 << log_size;
+    if (n_sets == 0) return 0;
+    fr_t beta_term = fr_ONE, delta_start;
+    fr_mul(&delta_start, beta, &fr_ZETA);
+    for (int64_t idx = 0; idx < isize; ++idx) {
+        int64_t r_next = (idx + rot_scale) % isize, r_last = (idx + (int64_t)last_rotation * rot_scale) % isize;
+        if (r_next < 0) r_next += isize;
+        if (r_last < 0) r_last += isize;
+        fr_t v = values[idx], t, u;
+#define FOLD(term) do { fr_mul(&v, &v, y); fr_add(&v, &v, (term)); } while (0)
+        fr_sub(&t, &fr_ONE, &z_cosets[0][idx]);
+        fr_mul(&t, &t, &l0[idx]);
+        FOLD(&t);
+        const fr_t *zl = &z_cosets[n_sets - 1][idx];
+        fr_sqr(&t, zl);
+        fr_sub(&t, &t, zl);
+        fr_mul(&t, &t, &l_last[idx]);
+        FOLD(&t);
+        for (uint32_t s = 1; s < n_sets; ++s) {
+            fr_sub(&t, &z_cosets[s][idx], &z_cosets[s - 1][r_last]);
+            fr_mul(&t, &t, &l0[idx]);
+            FOLD(&t);
+        }
+        fr_t current_delta;
+        fr_mul(&current_delta, &delta_start, &beta_term);
+        for (uint32_t s = 0; s < n_sets; ++s) {
+            uint32_t c0 = s * chunk_len, c1 = c0 + chunk_len;
+            if (c1 > n_cols) c1 = n_cols;
+            fr_t left = z_cosets[s][r_next], right = z_cosets[s][idx];
+            for (uint32_t j = c0; j < c1; ++j) {
+                fr_mul(&u, beta, &sigma_cosets[j][idx]);
+                fr_add(&u, &u, &value_cosets[j][idx]);
+                fr_add(&u, &u, gamma);
+                fr_mul(&left, &left, &u);
+            }
+            for (uint32_t j = c0; j < c1; ++j) {
+                fr_add(&u, &value_cosets[j][idx], &current_delta);
+                fr_add(&u, &u, gamma);
+                fr_mul(&right, &right, &u);
+                fr_mul(&current_delta, &current_delta, delta);
+            }
+            fr_sub(&t, &left, &right);
+            fr_mul(&t, &t, &l_active_row[idx]);
+            FOLD(&t);
+        }
+        values[idx] = v;
+        fr_mul(&beta_term, &beta_term, extended_omega);
+    }
+    return 0;
+}
+
+/* ---- evaluate_h, one log-derivative lookup (mv_lookup): phi_i = inputs_i + beta (the compressed input expressions,
+ * already evaluated on the coset), tau = table + beta:
+ *   inputs_prod = prod_i phi_i;  inputs_inv_sum = sum_i 1/phi_i  (BatchInvert: zero stays zero)
+ *   lhs = tau * inputs_prod * (phi[r_next] - phi[idx]);  rhs = inputs_prod * (tau * inputs_inv_sum - m[idx])
+ *   value = value*y + l0*phi;  value = value*y + l_last*phi;  value = value*y + (lhs - rhs) * l_active_row */
+int halo2_logup_h_terms(const fr_t *const *input_cosets, uint32_t n_inputs, const fr_t *table_coset, const fr_t *m_coset,
+                        const fr_t *phi_coset, const fr_t *l0, const fr_t *l_last, const fr_t *l_active_row, const fr_t *beta,
+                        const fr_t *y, fr_t *values, uint32_t log_size, int32_t rot_scale) {
+    const int64_t isize = (int64_t)1 << log_size;
+    fr_t *ph = (fr_t *)malloc(sizeof(fr_t) * (n_inputs ? n_inputs : 1)), *iv = (fr_t *)malloc(sizeof(fr_t) * (n_inputs ? n_inputs : 1));
+    fr_t *scratch = (fr_t *)malloc(sizeof(fr_t) * (n_inputs ? n_inputs : 1));
+    if (!ph || !iv || !scratch) return -1;
+    for (int64_t idx = 0; idx < isize; ++idx) {
+        int64_t r_next = (idx + rot_scale) % isize;
+        if (r_next < 0) r_next += isize;
+        fr_t prod = fr_ONE, inv_sum, tau, lhs, rhs, t, v = values[idx];
+        memset(&inv_sum, 0, sizeof inv_sum);
+        for (uint32_t i = 0; i < n_inputs; ++i) {
+            fr_add(&ph[i], &input_cosets[i][idx], beta);
+            iv[i] = ph[i];
+            fr_mul(&prod, &prod, &ph[i]);
+        }
+        fr_batch_invert(iv, n_inputs, scratch);
+        for (uint32_t i = 0; i < n_inputs; ++i) fr_add(&inv_sum, &inv_sum, &iv[i]);
+        fr_add(&tau, &table_coset[idx], beta);
+        fr_sub(&t, &phi_coset[r_next], &phi_coset[idx]);
+        fr_mul(&lhs, &tau, &prod);
+        fr_mul(&lhs, &lhs, &t);
+        fr_mul(&rhs, &tau, &inv_sum);
+        fr_sub(&rhs, &rhs, &m_coset[idx]);
+        fr_mul(&rhs, &rhs, &prod);
+        fr_mul(&t, &l0[idx], &phi_coset[idx]);
+        FOLD(&t);
+        fr_mul(&t, &l_last[idx], &phi_coset[idx]);
+        FOLD(&t);
+        fr_sub(&t, &lhs, &rhs);
+        fr_mul(&t, &t, &l_active_row[idx]);
+        FOLD(&t);
+        values[idx] = v;
+    }
+#undef FOLD
+    free(ph);
+    free(iv);
+    free(scratch);
+    return 0;
+}

@@ -488,3 +488,28 @@ def logup_running_sum(inputs, table, m, beta, k: int, phi_init) -> np.ndarray:
     rc = lib.halo2_logup_running_sum(ip, len(inputs), _p(t), _p(mm), _p(sc[0]), k, _p(sc[1]), _p(out))
     assert rc == 0
     return out
+
+
+def permutation_h_terms(z_cosets, chunk_len: int, value_cosets, sigma_cosets, l0, l_last, l_active_row, beta, gamma, y, delta,
+                        extended_omega, last_rotation: int, values, log_size: int, rot_scale: int) -> np.ndarray:
+    zp, _z = _colptrs(z_cosets)
+    vp, _v = _colptrs(value_cosets)
+    sp, _s = _colptrs(sigma_cosets)
+    ls = [np.ascontiguousarray(c, dtype=np.uint64) for c in (l0, l_last, l_active_row)]
+    sc = [np.ascontiguousarray(c, dtype=np.uint64) for c in (beta, gamma, y, delta, extended_omega)]
+    out = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    rc = lib.halo2_permutation_h_terms(zp, len(z_cosets), chunk_len, vp, sp, len(value_cosets), _p(ls[0]), _p(ls[1]), _p(ls[2]),
+                                       _p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(sc[4]), C.c_int32(last_rotation), _p(out),
+                                       log_size, C.c_int32(rot_scale))
+    assert rc == 0
+    return out
+
+
+def logup_h_terms(input_cosets, table_coset, m_coset, phi_coset, l0, l_last, l_active_row, beta, y, values, log_size: int,
+                  rot_scale: int) -> np.ndarray:
+    ip, _i = _colptrs(input_cosets)
+    cs = [np.ascontiguousarray(c, dtype=np.uint64) for c in (table_coset, m_coset, phi_coset, l0, l_last, l_active_row, beta, y)]
+    out = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    rc = lib.halo2_logup_h_terms(ip, len(input_cosets), *[_p(c) for c in cs], _p(out), log_size, C.c_int32(rot_scale))
+    assert rc == 0
+    return out

@@ -92,6 +92,7 @@ def _load():
         "b200zk_batch_invert": [vp, vp, u64],
         "b200zk_kate_division": [vp, vp, vp, u64, vp],
         "b200zk_prefix_scan": [vp, C.c_int, vp, u64, vp, vp],
+        "b200zk_poly_lincomb": [vp, vp, C.POINTER(vp), vp, u32, u64],
         "b200zk_permutation_product": [vp, C.POINTER(vp), C.POINTER(vp), u32, vp, vp, vp, vp, vp, u32, vp, vp],
         "b200zk_logup_running_sum": [vp, C.POINTER(vp), u32, vp, vp, vp, u32, vp, vp],
         "b200zk_graph_create": [vp, vp, u32, vp, u32, vp, u32, vp, u32, C.POINTER(vp)],
@@ -122,7 +123,7 @@ ABI_SYMBOLS = [
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
-    "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create",
+    "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_poly_lincomb", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create",
     "b200zk_graph_destroy", "b200zk_graph_info", "b200zk_graph_evaluate", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
@@ -326,6 +327,16 @@ class Context:
         pi, k2 = _ptr(init)
         po, k3 = _ptr(out)
         self._ck(lib().b200zk_prefix_scan(self._h, op, pa, n, pi, po))
+        return out
+
+    def poly_lincomb(self, polys, scalars, out):
+        """out = sum_j scalars[j] * polys[j] in one pass (device-resident polynomials)."""
+        n = _count(out, 32)
+        tp, kp = self._dev_table(polys)
+        sc = np.ascontiguousarray(np.asarray(scalars, dtype=np.uint64).reshape(-1, 4))
+        assert len(sc) == len(polys)
+        po, ko = _ptr(out)
+        self._ck(lib().b200zk_poly_lincomb(self._h, po, tp, C.c_void_p(sc.ctypes.data) if len(sc) else None, len(polys), n))
         return out
 
     def permutation_product(self, values, sigma, beta, gamma, delta_omega_start, delta, omega, k: int, z_init, out):

@@ -383,6 +383,31 @@ int32_t logup_running_sum_run(b200zk_ctx* ctx, const void* const* inputs, uint32
     return prefix_scan_run(ctx, B200ZK_SCAN_SUM, d, n, phi_init, phi_out, (Fr*)(base + o_scan));
 }
 
+// ------------------------------------------------------------------------------------------------ linear combination
+// out[i] = sum_j s_j * p_j[i]: every input is read once and the output written once (a chain of axpy calls would move
+// 3x the bytes).  The SHPLONK prover's  sum_i v^i p_i(X)  per rotation set, and the final L(X) combination.
+__global__ void __launch_bounds__(256) lincomb_kernel(const Fr* const* polys, const Fr* scalars, uint32_t count, uint64_t n, Fr* out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr acc = Fr::zero();
+        for (uint32_t j = 0; j < count; ++j) acc = acc + q_ld(scalars + j) * q_ld(polys[j] + i);
+        q_st(out + i, acc);
+    }
+}
+
+int32_t lincomb_run(b200zk_ctx* ctx, const void* const* polys, const Fr* scalars_host, uint32_t count, uint64_t n, Fr* out) {
+    size_t o_sc = 0, o_pt = sizeof(Fr) * ((size_t)count + 1);
+    B2_TRY(scratch_reserve(ctx, ctx->stage_out, o_pt + sizeof(void*) * ((size_t)count + 1)));
+    char* base = (char*)ctx->stage_out.p;
+    const Fr* const* dp;
+    B2_TRY(upload_ptrs(ctx, polys, count, base, o_pt, &dp));
+    if (count) B2_CUDA(ctx, cudaMemcpyAsync(base + o_sc, scalars_host, sizeof(Fr) * count, cudaMemcpyHostToDevice, ctx->stream));
+    ProfScope ps_(ctx, PROF_POLY);
+    lincomb_kernel<<<stream_blocks(ctx, n), 256, 0, ctx->stream>>>(dp, (const Fr*)(base + o_sc), count, n, out);
+    B2_LAUNCH_CHECK(ctx);
+    return B200ZK_OK;
+}
+
 }  // namespace b200zk
 
 using namespace b200zk;
@@ -402,6 +427,18 @@ static int32_t require_device_cols(b200zk_ctx* ctx, const void* const* cols, uin
 }
 
 extern "C" {
+
+int32_t b200zk_poly_lincomb(b200zk_ctx* ctx, void* out_dev, const void* const* polys_dev, const void* scalars32, uint32_t count, uint64_t n) {
+    CHECK_CTX(ctx);
+    if (count && !scalars32) return fail(ctx, B200ZK_E_INVALID, "poly_lincomb: null scalars");
+    Guard g(ctx);
+    if (!n) return B200ZK_OK;
+    B2_TRY(require_device(ctx, out_dev, "poly_lincomb: out"));
+    B2_TRY(require_device_cols(ctx, polys_dev, count, "poly_lincomb: polys"));
+    std::vector<Fr> sc(count + 1);
+    for (uint32_t j = 0; j < count; ++j) B2_TRY(read_fr(ctx, (const char*)scalars32 + 32 * (size_t)j, &sc[j]));
+    return lincomb_run(ctx, polys_dev, sc.data(), count, n, (Fr*)out_dev);
+}
 
 int32_t b200zk_prefix_scan(b200zk_ctx* ctx, int op, const void* in_dev, uint64_t n, const void* init32, void* out_dev) {
     CHECK_CTX(ctx);

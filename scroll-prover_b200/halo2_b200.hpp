@@ -11,6 +11,7 @@
 // A Rust panic (assert_eq!, unwrap) is mirrored by throwing halo2_b200::Panic.  Types are layout-identical to
 // halo2curves::bn256::{Fr, G1Affine, G1} (raw Montgomery limbs).  Header-only; link with -lb200zk.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -444,6 +445,82 @@ class GraphEvaluator {
     std::vector<int32_t> rotations_;
     b200zk_graph* graph_ = nullptr;
 };
+
+// evaluate_h's `// Permutations` section as a program appended to `ev` (upstream spells it out as a Rust loop; here the
+// same kernel serves gates, permutation and lookups).  z[s]: the permutation product cosets (advice-like sources at
+// rotation index 0 are re-issued at the next / last rotations); values[j] / sigma[j]: the permuted columns and their
+// sigma cosets; l0, l_last, l_active_row: the Lagrange cosets.  Folds into PreviousValue with y in upstream's order.
+inline ValueSource permutation_constraints(GraphEvaluator& ev, const std::vector<ValueSource>& z, uint32_t chunk_len,
+                                           const std::vector<ValueSource>& values, const std::vector<ValueSource>& sigma,
+                                           ValueSource l0, ValueSource l_last, ValueSource l_active_row, int32_t last_rotation,
+                                           const Fr& delta) {
+    if (z.empty() || values.size() != sigma.size()) throw Panic("permutation_constraints: bad shape");
+    const uint32_t r_next = ev.add_rotation(1), r_last = ev.add_rotation(last_rotation);
+    auto at = [](ValueSource s, uint32_t rot) { s.rotation = rot; return s; };
+    const ValueSource one = ev.add_constant(detail::from_dev(detail::DFr::one()));
+    std::vector<ValueSource> terms;
+    terms.push_back(ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_SUB, one, z.front()), l0));
+    ValueSource zl2 = ev.add(B200ZK_CALC_SQUARE, z.back());
+    terms.push_back(ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_SUB, zl2, z.back()), l_last));
+    for (size_t s = 1; s < z.size(); ++s)
+        terms.push_back(ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_SUB, z[s], at(z[s - 1], r_last)), l0));
+    const ValueSource bx = ev.add(B200ZK_CALC_MUL, ValueSource::Beta(), ValueSource::ExtendedX());  // beta * zeta * w_ext^idx
+    detail::DFr dpow = detail::DFr::one();
+    for (size_t s = 0; s < z.size(); ++s) {
+        size_t c0 = s * chunk_len, c1 = std::min(values.size(), c0 + chunk_len);
+        ValueSource left = at(z[s], r_next), right = z[s];
+        for (size_t j = c0; j < c1; ++j) {
+            ValueSource u = ev.add(B200ZK_CALC_MUL, ValueSource::Beta(), sigma[j]);
+            u = ev.add(B200ZK_CALC_ADD, u, values[j]);
+            u = ev.add(B200ZK_CALC_ADD, u, ValueSource::Gamma());
+            left = ev.add(B200ZK_CALC_MUL, left, u);
+        }
+        for (size_t j = c0; j < c1; ++j) {
+            ValueSource d = (j == 0) ? bx : ev.add(B200ZK_CALC_MUL, bx, ev.add_constant(detail::from_dev(dpow)));
+            ValueSource u = ev.add(B200ZK_CALC_ADD, values[j], d);
+            u = ev.add(B200ZK_CALC_ADD, u, ValueSource::Gamma());
+            right = ev.add(B200ZK_CALC_MUL, right, u);
+            dpow = dpow * detail::to_dev(delta);
+        }
+        terms.push_back(ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_SUB, left, right), l_active_row));
+    }
+    return ev.add_horner(ValueSource::PreviousValue(), terms, ValueSource::Y());
+}
+
+// evaluate_h's section for one log-derivative lookup: inputs[i] = compressed input expressions, table, m, phi on the coset.
+// rhs uses the polynomial form tau * sum_i prod_{j != i} (f_j + beta) - m * prod (no per-row inversion).
+inline ValueSource lookup_constraints(GraphEvaluator& ev, const std::vector<ValueSource>& inputs, ValueSource table, ValueSource m,
+                                      ValueSource phi, ValueSource l0, ValueSource l_last, ValueSource l_active_row) {
+    const uint32_t r_next = ev.add_rotation(1);
+    const ValueSource one = ev.add_constant(detail::from_dev(detail::DFr::one()));
+    const ValueSource zero = ev.add_constant(detail::from_dev(detail::DFr::zero()));
+    const size_t n = inputs.size();
+    std::vector<ValueSource> ph(n), pre(n, one), suf(n, one);
+    for (size_t i = 0; i < n; ++i) ph[i] = ev.add(B200ZK_CALC_ADD, inputs[i], ValueSource::Beta());
+    ValueSource prod = one;
+    for (size_t i = 0; i < n; ++i) {
+        pre[i] = prod;
+        prod = (i == 0) ? ph[0] : ev.add(B200ZK_CALC_MUL, prod, ph[i]);
+    }
+    ValueSource acc = one;
+    for (size_t i = n; i-- > 0;) {
+        suf[i] = acc;
+        acc = (i + 1 == n) ? ph[i] : ev.add(B200ZK_CALC_MUL, acc, ph[i]);
+    }
+    ValueSource ssum = zero;
+    for (size_t i = 0; i < n; ++i) {
+        ValueSource term = (i == 0) ? suf[i] : (i + 1 == n) ? pre[i] : ev.add(B200ZK_CALC_MUL, pre[i], suf[i]);
+        ssum = (i == 0) ? term : ev.add(B200ZK_CALC_ADD, ssum, term);
+    }
+    ValueSource phi_next = phi;
+    phi_next.rotation = r_next;
+    ValueSource tau = ev.add(B200ZK_CALC_ADD, table, ValueSource::Beta());
+    ValueSource lhs = ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_MUL, tau, prod), ev.add(B200ZK_CALC_SUB, phi_next, phi));
+    ValueSource rhs = ev.add(B200ZK_CALC_SUB, ev.add(B200ZK_CALC_MUL, tau, ssum), ev.add(B200ZK_CALC_MUL, m, prod));
+    ValueSource q = ev.add(B200ZK_CALC_MUL, ev.add(B200ZK_CALC_SUB, lhs, rhs), l_active_row);
+    return ev.add_horner(ValueSource::PreviousValue(), {ev.add(B200ZK_CALC_MUL, l0, phi), ev.add(B200ZK_CALC_MUL, l_last, phi), q},
+                         ValueSource::Y());
+}
 
 // permutation::Argument::commit, one column set: z in Lagrange form (the caller applies the blinding rows and chains
 // z[n - (blinding_factors + 1)] into the next set as z_init, as upstream does)

@@ -279,3 +279,20 @@ def test_prefix_product_full_size_telescopes(ctx):
     # back[i] = total * prod_{j<i} a_j^-1  =>  back[n-1] * a[n-1]^-1 = init
     fin = O.fr_mul(host(back[n - 1:n])[0], host(inv[n - 1:n])[0])
     assert np.array_equal(fin, init)
+
+
+@pytest.mark.parametrize("count,n", [(1, 1), (3, 1000), (8, 1 << 14), (0, 64)])
+def test_poly_lincomb_matches_bigint(ctx, count, n):
+    """out = sum_j s_j p_j in one pass (the SHPLONK prover's per-rotation-set combination), also with out aliasing p_0"""
+    polys = [O.fill_fr(n, 800 + j) for j in range(count)]
+    sc = O.fill_fr(max(count, 1), 900)[:count]
+    pi = [O.frs_to_ints(p) for p in polys]
+    si = O.frs_to_ints(sc)
+    want = [sum(s * p[i] for s, p in zip(si, pi)) % R_MOD for i in range(n)]
+    d = [dev(p) for p in polys]
+    out = dev(np.zeros((n, 4), np.uint64))
+    ctx.poly_lincomb(d, sc, out)
+    assert O.frs_to_ints(host(out)) == want
+    if count:
+        ctx.poly_lincomb(d, sc, d[0])
+        assert O.frs_to_ints(host(d[0])) == want
