@@ -296,3 +296,31 @@ def test_poly_lincomb_matches_bigint(ctx, count, n):
     if count:
         ctx.poly_lincomb(d, sc, d[0])
         assert O.frs_to_ints(host(d[0])) == want
+
+
+@pytest.mark.parametrize("n", [1, 63, 2047, 2048, 2049, 4097, 131071, 131072 + 64, (1 << 20) + 5, 1 << 22])
+def test_batch_invert_levels_and_zeros(ctx, n):
+    """hierarchical Montgomery trick: sizes around the leaf (2048) and slice (64) boundaries, zeros (isolated, a whole strided
+    slice, the first and last element) stay zero; checked element-wise against the oracle, larger sizes by a * a^-1 = 1"""
+    a = O.fill_fr(n, 5000 + n)
+    z = np.zeros(4, np.uint64)
+    if n > 1:
+        a[0] = z
+        a[n - 1] = z
+        a[n // 2] = z
+    if n > 4096:
+        T = (n + 63) // 64
+        a[7::T] = z  # every element of one thread's strided slice
+    d = dev(a)
+    ctx.batch_invert(d)
+    got = host(d)
+    zero_rows = ~a.any(axis=1)
+    assert not got[zero_rows].any()
+    if n <= 4097:
+        assert np.array_equal(got, O.fr_batch_invert(a))
+    else:
+        prod = host(ctx.poly_mul(d, dev(a)))
+        one = O.fr_from_int(1)
+        assert np.array_equal(prod[~zero_rows], np.broadcast_to(one, (int((~zero_rows).sum()), 4)))
+        idx = np.arange(0, n, max(1, n // 64))
+        assert np.array_equal(got[idx], O.fr_batch_invert(a[idx]))
