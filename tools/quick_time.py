@@ -81,7 +81,13 @@ def main():
         ctx.profile_enable(True); ctx.profile_reset(); srs.msm(wl); profw = ctx.profile_read(); ctx.profile_enable(False)
         out[-1]["witness_like_ms"] = bw
         out[-1]["witness_like_prof"] = {k: round(v["ms"], 4) for k, v in profw.items() if v["count"]}
-        print(json.dumps({"op": "msm_witness_like", "log_n": log_n, "ms_best": bw, "prof": out[-1]["witness_like_prof"]}), flush=True)
+        ctx.msm_total_adds(reset=True)
+        srs.msm(wl)
+        ctx.synchronize()
+        adds = ctx.msm_total_adds(reset=True)  # non-zero signed digits actually accumulated
+        print(json.dumps({"op": "msm_witness_like", "log_n": log_n, "ms_best": bw, "c": st["window_bits"], "W": st["n_windows"],
+                          "actual_adds": adds, "Gadds_s": adds / bw / 1e6, "Mpoints_s": n / bw / 1e3,
+                          "prof": out[-1]["witness_like_prof"]}), flush=True)
         srs.release()
         del g
     json.dump(out, open("gpurun_out/quick_time.json", "w"), indent=1)
