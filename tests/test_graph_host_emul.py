@@ -177,3 +177,25 @@ def test_too_many_live_intermediates_is_reported(lib):
     rc, _, _, err = host_eval(lib, calcs, O.frs_from_ints([1]), [0], [], [O.fill_fr(2, 1)], [], e, [z, z, z, z], None,
                               np.zeros((2, 4), np.uint64), 1, 1)
     assert rc == -1 and "too many intermediates" in err
+
+
+def test_many_random_small_programs(lib):
+    """300 random programs of every shape (operand sharing, Horner with repeated / empty parts, dead code, results that are
+    plain sources): the lowered program must equal the oracle's straight evaluation, row for row."""
+    rng = random.Random(20260922)
+    for trial in range(300):
+        n_calcs = rng.randrange(1, 70)
+        bias = rng.choice([0.0, 0.2, 0.5, 0.8, 0.95])
+        log_size = rng.choice([0, 1, 2, 3])
+        rot_scale = rng.choice([1, 2, 4])
+        calcs, constants, rotations = random_program(1000 + trial, n_calcs, 1, 2, 1, 1, rng.randrange(1, 5), n_constants=3,
+                                                     use_prev=rng.random() < 0.7, use_x=rng.random() < 0.5, chain_bias=bias)
+        size = 1 << log_size
+        fx, ad, ins, ch, bgty, prev = inputs(trial, size, 1, 2, 1, 1)
+        w = O.fr_from_int(omega_of(log_size))
+        consts = O.frs_from_ints(constants)
+        want = O.graph_evaluate(calcs, consts, rotations, fx, ad, ins, ch, *bgty, w, prev, log_size, rot_scale)
+        rc, got, (n_instr, n_slots), err = host_eval(lib, calcs, consts, rotations, fx, ad, ins, ch, bgty, w, prev, log_size, rot_scale)
+        assert rc == 0, (trial, err)
+        assert np.array_equal(got, want), trial
+        assert n_slots <= 2 + n_calcs
