@@ -240,6 +240,12 @@ B200ZK_API int32_t b200zk_graph_create(b200zk_ctx* ctx, const b200zk_calculation
                                        const b200zk_value_source* horner_parts, uint32_t n_parts, const void* constants32,
                                        uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations,
                                        b200zk_graph** out);
+/* The validation and lowering of b200zk_graph_create alone -- no context, no device: lets the key-generation side check
+ * a program (and read its instruction / slot count) on a machine without a GPU.  message receives the reason on failure. */
+B200ZK_API int32_t b200zk_graph_check(const b200zk_calculation* calculations, uint32_t n_calculations,
+                                      const b200zk_value_source* horner_parts, uint32_t n_parts, uint32_t n_constants,
+                                      uint32_t n_rotations, uint32_t* n_instructions, uint32_t* n_slots, char* message,
+                                      uint64_t message_cap);
 B200ZK_API int32_t b200zk_graph_destroy(b200zk_ctx* ctx, b200zk_graph* graph);
 B200ZK_API int32_t b200zk_graph_info(const b200zk_graph* graph, uint32_t* n_instructions, uint32_t* n_slots);
 /* GraphEvaluator::evaluate for every row of the extended domain: values[row] = result of the last calculation, with

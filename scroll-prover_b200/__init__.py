@@ -96,6 +96,7 @@ def _load():
         "b200zk_permutation_product": [vp, C.POINTER(vp), C.POINTER(vp), u32, vp, vp, vp, vp, vp, u32, vp, vp],
         "b200zk_logup_running_sum": [vp, C.POINTER(vp), u32, vp, vp, vp, u32, vp, vp],
         "b200zk_graph_create": [vp, vp, u32, vp, u32, vp, u32, vp, u32, C.POINTER(vp)],
+        "b200zk_graph_check": [vp, u32, vp, u32, u32, u32, C.POINTER(u32), C.POINTER(u32), C.c_char_p, u64],
         "b200zk_graph_destroy": [vp, vp],
         "b200zk_graph_info": [vp, C.POINTER(u32), C.POINTER(u32)],
         "b200zk_graph_evaluate": [vp, vp, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp), u32, vp, u32, vp, vp, vp, vp, vp,
@@ -123,7 +124,7 @@ ABI_SYMBOLS = [
     "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
-    "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_poly_lincomb", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create",
+    "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_poly_lincomb", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create", "b200zk_graph_check",
     "b200zk_graph_destroy", "b200zk_graph_info", "b200zk_graph_evaluate", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
@@ -489,6 +490,32 @@ SRC_CONSTANT, SRC_INTERMEDIATE, SRC_FIXED, SRC_ADVICE, SRC_INSTANCE, SRC_CHALLEN
     SRC_PREVIOUS_VALUE, SRC_EXTENDED_X = range(12)
 CALC_ADD, CALC_SUB, CALC_MUL, CALC_SQUARE, CALC_DOUBLE, CALC_NEGATE, CALC_HORNER, CALC_STORE = range(8)
 SCAN_PRODUCT, SCAN_SUM = 0, 1
+
+
+def _pack_calcs(calcs):
+    parts = []
+    arr = (_Calculation * max(1, len(calcs)))()
+    for i, (op, a, b, ps) in enumerate(calcs):
+        arr[i].op = op
+        arr[i].a = _ValueSource(*a)
+        arr[i].b = _ValueSource(*(b if b is not None else (0, 0, 0)))
+        arr[i].parts_offset = len(parts)
+        arr[i].parts_len = len(ps or [])
+        parts.extend(ps or [])
+    parr = (_ValueSource * max(1, len(parts)))(*[_ValueSource(*q) for q in parts])
+    return arr, parr, len(parts)
+
+
+def graph_check(calcs, n_constants: int, n_rotations: int) -> dict:
+    """b200zk_graph_check: validate + lower a program without a context or a device; raises B200zkError with the reason."""
+    arr, parr, n_parts = _pack_calcs(calcs)
+    ni, ns = C.c_uint32(), C.c_uint32()
+    msg = C.create_string_buffer(256)
+    rc = lib().b200zk_graph_check(C.cast(arr, C.c_void_p), len(calcs), C.cast(parr, C.c_void_p), n_parts, n_constants, n_rotations,
+                                  C.byref(ni), C.byref(ns), msg, 256)
+    if rc != OK:
+        raise B200zkError(rc, msg.value.decode())
+    return {"n_instructions": ni.value, "n_slots": ns.value}
 
 
 class Graph:

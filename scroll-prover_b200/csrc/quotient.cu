@@ -568,6 +568,22 @@ int32_t b200zk_graph_info(const b200zk_graph* graph, uint32_t* n_instructions, u
     return B200ZK_OK;
 }
 
+int32_t b200zk_graph_check(const b200zk_calculation* calculations, uint32_t n_calculations, const b200zk_value_source* horner_parts,
+                           uint32_t n_parts, uint32_t n_constants, uint32_t n_rotations, uint32_t* n_instructions, uint32_t* n_slots,
+                           char* message, uint64_t message_cap) {
+    if (message && message_cap) message[0] = 0;
+    if ((n_calculations && !calculations) || (n_parts && !horner_parts)) return B200ZK_E_INVALID;
+    GraphProgram prog;
+    std::string err = graph_compile(calculations, n_calculations, horner_parts, n_parts, n_constants, n_rotations, &prog);
+    if (!err.empty()) {
+        if (message && message_cap) snprintf(message, (size_t)message_cap, "%s", err.c_str());
+        return err.find("too many intermediates") != std::string::npos ? B200ZK_E_UNSUPPORTED : B200ZK_E_INVALID;
+    }
+    if (n_instructions) *n_instructions = (uint32_t)prog.instrs.size();
+    if (n_slots) *n_slots = prog.n_slots;
+    return B200ZK_OK;
+}
+
 int32_t b200zk_graph_evaluate(b200zk_ctx* ctx, const b200zk_graph* graph, const void* const* fixed_dev, uint32_t n_fixed,
                               const void* const* advice_dev, uint32_t n_advice, const void* const* instance_dev, uint32_t n_instance,
                               const void* challenges32, uint32_t n_challenges, const void* beta32, const void* gamma32,
