@@ -57,6 +57,7 @@ struct b200zk_ctx {
     int sm_count = 148;
     // scratch pools
     b200zk::Scratch ntt_work, stage_in, stage_out, msm_work, misc;
+    b200zk::Scratch msm_affine_work;  // point / prefix arrays of the experimental batched-affine accumulation (msm_affine.cu)
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<b200zk::TwiddleTable> tables;
@@ -77,6 +78,7 @@ struct b200zk_ctx {
     uint32_t msm_window = 0;
     uint32_t msm_scatter_sweeps = 0;
     uint32_t msm_acc_l = 0;
+    int msm_affine = 0;      // 1: batched-affine bucket accumulation (experimental, B200ZK_MSM_AFFINE); 0: XYZZ lock-step chunks
     int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;
