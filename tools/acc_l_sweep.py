@@ -11,8 +11,9 @@ import sys
 
 import torch
 
-sys.path.insert(0, "/root/repo")
-sys.path.insert(0, "/root/repo/tools")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tools"))
 zk = importlib.import_module("scroll-prover_b200")
 from quick_time import rand_fr, timeit  # noqa: E402
 

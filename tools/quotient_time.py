@@ -4,13 +4,15 @@ usage: quotient_time.py [k]     (default 22: columns of 2^k rows, extended domai
 """
 import importlib
 import json
+import os
 import sys
 
 import torch
 
-sys.path.insert(0, "/root/repo")
-sys.path.insert(0, "/root/repo/tools")
-sys.path.insert(0, "/root/repo/tests")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tools"))
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
 zk = importlib.import_module("scroll-prover_b200")
 from quick_time import rand_fr, timeit  # noqa: E402
 from quotient_programs import (C_ADD, C_HORNER, C_MUL, C_SUB, DELTA, S_ADVICE, S_CONST, S_FIXED, S_INTER, S_PREV, S_Y, omega_of)  # noqa: E402

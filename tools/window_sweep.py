@@ -5,13 +5,15 @@ csrc/msm.cu can be checked against measurements.  usage: window_sweep.py "14,16,
 """
 import importlib
 import json
+import os
 import sys
 
 import torch
 
-sys.path.insert(0, "/root/repo")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT)
 zk = importlib.import_module("scroll-prover_b200")
-sys.path.insert(0, "/root/repo/tools")
+sys.path.insert(0, os.path.join(_ROOT, "tools"))
 from quick_time import rand_fr, timeit  # noqa: E402
 
 
