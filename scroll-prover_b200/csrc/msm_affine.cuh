@@ -60,6 +60,28 @@ FF_HD void ba_store(Affine* p, const Affine& v) {
 #endif
 }
 
+FF_HD Fq ba_load_fq(const Fq* p) {
+#ifdef __CUDA_ARCH__
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fq r;
+    r.l.v[0] = a.x; r.l.v[1] = a.y; r.l.v[2] = a.z; r.l.v[3] = a.w;
+    r.l.v[4] = b.x; r.l.v[5] = b.y; r.l.v[6] = b.z; r.l.v[7] = b.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+FF_HD void ba_store_fq(Fq* p, const Fq& v) {
+#ifdef __CUDA_ARCH__
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l.v[0], v.l.v[1], v.l.v[2], v.l.v[3]);
+    q[1] = make_uint4(v.l.v[4], v.l.v[5], v.l.v[6], v.l.v[7]);
+#else
+    *p = v;
+#endif
+}
+
 // input `pos` of a level: a signed base at level 0, a stored partial sum above
 FF_HD Affine ba_input(const BaLevel& lv, uint32_t pos) {
     if (lv.entries) {
@@ -127,7 +149,7 @@ FF_HD void ba_thread_a(uint64_t t, uint32_t L, const BaLevel& lv, Fq* prefix, Fq
     const uint32_t M = lv.off_out[lv.NB];
     uint64_t start = t * (uint64_t)L;
     if (start >= M) {
-        totals[t] = Fq::one();  // the launch covers an upper bound of M: idle threads must not poison the shared inversion
+        ba_store_fq(totals + t, Fq::one());  // the launch covers an upper bound of M: idle threads must not poison the shared inversion
         return;
     }
     uint32_t end = (start + L < M) ? (uint32_t)(start + L) : M;
@@ -141,10 +163,10 @@ FF_HD void ba_thread_a(uint64_t t, uint32_t L, const BaLevel& lv, Fq* prefix, Fq
         if (has_b) pb = ba_input(lv, i0 + 1);
         Fq d;
         ba_classify(pa, pb, has_b, d);
-        prefix[o] = acc;
+        ba_store_fq(prefix + o, acc);
         if (!d.is_zero()) acc = acc * d;
     }
-    totals[t] = acc;
+    ba_store_fq(totals + t, acc);
 }
 
 // pass B of thread t: inv_totals[t] = 1 / totals[t]; walks the same slots backwards and writes the sums
@@ -154,7 +176,7 @@ FF_HD void ba_thread_b(uint64_t t, uint32_t L, const BaLevel& lv, const Fq* pref
     if (start >= M) return;
     uint32_t end = (start + L < M) ? (uint32_t)(start + L) : M;
     uint64_t b = ba_find_bucket(lv.off_out, lv.NB, end - 1);
-    Fq acc = inv_totals[t];
+    Fq acc = ba_load_fq(inv_totals + t);
     for (uint32_t o = end; o-- > (uint32_t)start;) {
         while (o < lv.off_out[b]) --b;
         uint32_t j = o - lv.off_out[b], m_in = lv.off_in[b + 1] - lv.off_in[b], i0 = lv.off_in[b] + 2 * j;
@@ -164,7 +186,7 @@ FF_HD void ba_thread_b(uint64_t t, uint32_t L, const BaLevel& lv, const Fq* pref
         Fq d, inv_d = Fq::zero();
         int kind = ba_classify(pa, pb, has_b, d);
         if (!d.is_zero()) {
-            inv_d = prefix[o] * acc;  // (d_0 .. d_{o-1}) * (d_0 .. d_o)^-1
+            inv_d = ba_load_fq(prefix + o) * acc;  // (d_0 .. d_{o-1}) * (d_0 .. d_o)^-1
             acc = acc * d;
         }
         ba_store(out + o, ba_combine(kind, pa, pb, inv_d));
