@@ -78,6 +78,7 @@ struct b200zk_ctx {
     uint32_t msm_window = 0;
     uint32_t msm_scatter_sweeps = 0;
     uint32_t msm_acc_l = 0;
+    uint32_t msm_affine_l = 0;  // output slots per thread of the batched-affine levels (0 = default)
     int msm_affine = 0;      // 1: batched-affine bucket accumulation (experimental, B200ZK_MSM_AFFINE); 0: XYZZ lock-step chunks
     int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed

@@ -9,16 +9,17 @@
 
 namespace b200zk {
 
-constexpr uint32_t BA_L = 16;  // output slots per thread (the inversion is shared by 16 additions per thread, then by the
-                               // hierarchical inversion of the thread totals)
+constexpr uint32_t BA_L_DEFAULT = 16;  // output slots per thread: the inversion is shared by L additions per thread, then by the
+                                       // hierarchical inversion of the thread totals (B200ZK_AFFINE_L overrides, for tuning)
 
-__global__ void __launch_bounds__(128) ba_pass_a(BaLevel lv, Fq* prefix, Fq* totals, uint64_t nthreads) {
+__global__ void __launch_bounds__(128) ba_pass_a(BaLevel lv, Fq* prefix, Fq* totals, uint64_t nthreads, uint32_t L) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nthreads) ba_thread_a(t, BA_L, lv, prefix, totals);
+    if (t < nthreads) ba_thread_a(t, L, lv, prefix, totals);
 }
-__global__ void __launch_bounds__(128) ba_pass_b(BaLevel lv, const Fq* prefix, const Fq* inv_totals, Affine* out, uint64_t nthreads) {
+__global__ void __launch_bounds__(128) ba_pass_b(BaLevel lv, const Fq* prefix, const Fq* inv_totals, Affine* out, uint64_t nthreads,
+                                                 uint32_t L) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nthreads) ba_thread_b(t, BA_L, lv, prefix, inv_totals, out);
+    if (t < nthreads) ba_thread_b(t, L, lv, prefix, inv_totals, out);
 }
 __global__ void __launch_bounds__(256) ba_finalize(BaLevel lv, XYZZ* buckets) {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,6 +137,7 @@ static size_t ba_invert_scratch_elems(uint64_t n) {
 // thread totals with their inversion scratch, two offset arrays and the scan tiles.
 int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32_t* entries, const uint32_t* offsets, uint64_t NB,
                               uint64_t max_entries, XYZZ* buckets) {
+    const uint32_t BA_L = ctx->msm_affine_l ? ctx->msm_affine_l : BA_L_DEFAULT;
     const uint64_t cap1 = max_entries / 2 + NB + 1;  // outputs of the first level: sum_b ceil(m_b / 2) <= M/2 + NB
     const uint64_t tcap = (cap1 + BA_L - 1) / BA_L;
     const uint32_t ntiles = (uint32_t)((NB + BA_SCAN_TILE - 1) / BA_SCAN_TILE);
@@ -177,11 +179,11 @@ int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32
         if (out_bound > cap1) out_bound = cap1;
         uint64_t nthreads = (out_bound + BA_L - 1) / BA_L;
         uint32_t blocks = (uint32_t)((nthreads + 127) / 128);
-        ba_pass_a<<<blocks, 128, 0, st>>>(lv, prefix, totals, nthreads);
+        ba_pass_a<<<blocks, 128, 0, st>>>(lv, prefix, totals, nthreads, BA_L);
         B2_LAUNCH_CHECK(ctx);
         // (threads past the real output count write a total of one, so the shared inversion stays well defined)
         B2_TRY(ba_invert_totals(ctx, totals, nthreads, inv_scratch));
-        ba_pass_b<<<blocks, 128, 0, st>>>(lv, prefix, totals, out, nthreads);
+        ba_pass_b<<<blocks, 128, 0, st>>>(lv, prefix, totals, out, nthreads, BA_L);
         B2_LAUNCH_CHECK(ctx);
         lv.entries = nullptr;
         lv.points = out;
