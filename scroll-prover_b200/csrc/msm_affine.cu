@@ -12,7 +12,10 @@ namespace b200zk {
 constexpr uint32_t BA_L_DEFAULT = 16;  // output slots per thread: the inversion is shared by L additions per thread, then by the
                                        // hierarchical inversion of the thread totals (B200ZK_AFFINE_L overrides, for tuning)
 
-__global__ void __launch_bounds__(128) ba_pass_a(BaLevel lv, Fq* prefix, Fq* totals, uint64_t nthreads, uint32_t L) {
+// `active` (written by ba_scan_tiles): 0 when the level has no pair left to add -- it only copies single points, so the
+// prefix products and the inversion are skipped (pass B never reads them for copies) and the level costs a few empty launches
+__global__ void __launch_bounds__(128) ba_pass_a(BaLevel lv, Fq* prefix, Fq* totals, uint64_t nthreads, uint32_t L, const uint32_t* active) {
+    if (!*active) return;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nthreads) ba_thread_a(t, L, lv, prefix, totals);
 }
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(BA_SCAN_TPB) ba_next_counts_tiles(const uint32
     }
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = sh[0];
 }
-__global__ void ba_scan_tiles(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total) {
+__global__ void ba_scan_tiles(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total, const uint32_t* in_total, uint32_t* active) {
     if (threadIdx.x || blockIdx.x) return;
     uint32_t acc = 0;
     for (uint32_t i = 0; i < ntiles; ++i) {
@@ -51,6 +54,7 @@ __global__ void ba_scan_tiles(uint32_t* tile_sums, uint32_t ntiles, uint32_t* gr
         acc += v;
     }
     *grand_total = acc;  // off_out[NB]
+    *active = acc < *in_total;  // some bucket still holds two or more points
 }
 __global__ void __launch_bounds__(BA_SCAN_TPB) ba_next_offsets(const uint32_t* off_in, uint64_t NB, const uint32_t* tile_offs, uint32_t* off_out) {
     __shared__ uint32_t sh[BA_SCAN_TPB];
@@ -78,7 +82,8 @@ __global__ void __launch_bounds__(BA_SCAN_TPB) ba_next_offsets(const uint32_t* o
 
 // ---- inversion of the thread totals (Fq): the same hierarchical Montgomery trick as poly.cu's batch_invert, on Fq
 constexpr uint64_t BAI_SLICE = 64, BAI_LEAF = 2048;
-__global__ void __launch_bounds__(256) bai_up(const Fq* data, Fq* prefix, Fq* totals, uint64_t n, uint32_t T) {
+__global__ void __launch_bounds__(256) bai_up(const Fq* data, Fq* prefix, Fq* totals, uint64_t n, uint32_t T, const uint32_t* active) {
+    if (!*active) return;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     Fq acc = Fq::one();
@@ -88,7 +93,8 @@ __global__ void __launch_bounds__(256) bai_up(const Fq* data, Fq* prefix, Fq* to
     }
     totals[t] = acc;
 }
-__global__ void __launch_bounds__(256) bai_down(Fq* data, const Fq* prefix, const Fq* inv_totals, uint64_t n, uint32_t T) {
+__global__ void __launch_bounds__(256) bai_down(Fq* data, const Fq* prefix, const Fq* inv_totals, uint64_t n, uint32_t T, const uint32_t* active) {
+    if (!*active) return;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T || t >= n) return;
     uint64_t cnt = (n - t + T - 1) / T;
@@ -100,23 +106,24 @@ __global__ void __launch_bounds__(256) bai_down(Fq* data, const Fq* prefix, cons
         acc = acc * v;
     }
 }
-__global__ void __launch_bounds__(128) bai_leaf(Fq* data, uint64_t n) {
+__global__ void __launch_bounds__(128) bai_leaf(Fq* data, uint64_t n, const uint32_t* active) {
+    if (!*active) return;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) data[i] = data[i].inv();
 }
-static int32_t ba_invert_totals(b200zk_ctx* ctx, Fq* data, uint64_t n, Fq* scratch) {
+static int32_t ba_invert_totals(b200zk_ctx* ctx, Fq* data, uint64_t n, Fq* scratch, const uint32_t* active) {
     if (n <= BAI_LEAF) {
-        bai_leaf<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(data, n);
+        bai_leaf<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(data, n, active);
         B2_LAUNCH_CHECK(ctx);
         return B200ZK_OK;
     }
     uint64_t T = (n + BAI_SLICE - 1) / BAI_SLICE;
     Fq *prefix = scratch, *totals = scratch + n;
     uint32_t blocks = (uint32_t)((T + 255) / 256);
-    bai_up<<<blocks, 256, 0, ctx->stream>>>(data, prefix, totals, n, (uint32_t)T);
+    bai_up<<<blocks, 256, 0, ctx->stream>>>(data, prefix, totals, n, (uint32_t)T, active);
     B2_LAUNCH_CHECK(ctx);
-    B2_TRY(ba_invert_totals(ctx, totals, T, totals + T));
-    bai_down<<<blocks, 256, 0, ctx->stream>>>(data, prefix, totals, n, (uint32_t)T);
+    B2_TRY(ba_invert_totals(ctx, totals, T, totals + T, active));
+    bai_down<<<blocks, 256, 0, ctx->stream>>>(data, prefix, totals, n, (uint32_t)T, active);
     B2_LAUNCH_CHECK(ctx);
     return B200ZK_OK;
 }
@@ -145,13 +152,14 @@ int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
     size_t o_p0 = carve(sizeof(Affine) * cap1), o_p1 = carve(sizeof(Affine) * cap1), o_prefix = carve(sizeof(Fq) * cap1);
     size_t o_tot = carve(sizeof(Fq) * (tcap + 1)), o_inv = carve(sizeof(Fq) * ba_invert_scratch_elems(tcap));
-    size_t o_off0 = carve(4 * (NB + 1)), o_off1 = carve(4 * (NB + 1)), o_tiles = carve(4 * ((size_t)ntiles + 1));
+    size_t o_off0 = carve(4 * (NB + 1)), o_off1 = carve(4 * (NB + 1)), o_tiles = carve(4 * ((size_t)ntiles + 1)), o_flag = carve(256);
     B2_TRY(scratch_reserve(ctx, ctx->msm_affine_work, off));
     char* base = (char*)ctx->msm_affine_work.p;
     Affine* pts[2] = {(Affine*)(base + o_p0), (Affine*)(base + o_p1)};
     uint32_t* offs[2] = {(uint32_t*)(base + o_off0), (uint32_t*)(base + o_off1)};
     Fq *prefix = (Fq*)(base + o_prefix), *totals = (Fq*)(base + o_tot), *inv_scratch = (Fq*)(base + o_inv);
     uint32_t* tiles = (uint32_t*)(base + o_tiles);
+    uint32_t* active = (uint32_t*)(base + o_flag);
     cudaStream_t st = ctx->stream;
 
     // a bucket of m entries needs ceil(log2 m) levels; m <= max_entries.  Levels past a bucket's last addition only copy its
@@ -170,7 +178,7 @@ int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32
         Affine* out = pts[l & 1];
         ba_next_counts_tiles<<<ntiles, BA_SCAN_TPB, 0, st>>>(lv.off_in, NB, tiles);
         B2_LAUNCH_CHECK(ctx);
-        ba_scan_tiles<<<1, 32, 0, st>>>(tiles, ntiles, off_out + NB);
+        ba_scan_tiles<<<1, 32, 0, st>>>(tiles, ntiles, off_out + NB, lv.off_in + NB, active);
         B2_LAUNCH_CHECK(ctx);
         ba_next_offsets<<<ntiles, BA_SCAN_TPB, 0, st>>>(lv.off_in, NB, tiles, off_out);
         B2_LAUNCH_CHECK(ctx);
@@ -179,10 +187,10 @@ int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32
         if (out_bound > cap1) out_bound = cap1;
         uint64_t nthreads = (out_bound + BA_L - 1) / BA_L;
         uint32_t blocks = (uint32_t)((nthreads + 127) / 128);
-        ba_pass_a<<<blocks, 128, 0, st>>>(lv, prefix, totals, nthreads, BA_L);
+        ba_pass_a<<<blocks, 128, 0, st>>>(lv, prefix, totals, nthreads, BA_L, active);
         B2_LAUNCH_CHECK(ctx);
         // (threads past the real output count write a total of one, so the shared inversion stays well defined)
-        B2_TRY(ba_invert_totals(ctx, totals, nthreads, inv_scratch));
+        B2_TRY(ba_invert_totals(ctx, totals, nthreads, inv_scratch, active));
         ba_pass_b<<<blocks, 128, 0, st>>>(lv, prefix, totals, out, nthreads, BA_L);
         B2_LAUNCH_CHECK(ctx);
         lv.entries = nullptr;

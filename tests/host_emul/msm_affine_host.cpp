@@ -29,8 +29,14 @@ extern "C" int msm_affine_host(const Affine* bases, const uint32_t* entries, con
         uint64_t out_bound = bound / 2 + NB + 1;
         if (out_bound > cap1) out_bound = cap1;
         uint64_t nthreads = (out_bound + L - 1) / L;
-        for (uint64_t t = 0; t < nthreads; ++t) ba_thread_a(t, L, lv, prefix.data(), totals.data());
-        for (uint64_t t = 0; t < nthreads; ++t) totals[t] = totals[t].inv();  // ba_invert_totals
+        const bool active = acc < lv.off_in[NB];  // ba_scan_tiles' flag: inactive levels skip pass A and the inversion
+        if (active) {
+            for (uint64_t t = 0; t < nthreads; ++t) ba_thread_a(t, L, lv, prefix.data(), totals.data());
+            for (uint64_t t = 0; t < nthreads; ++t) totals[t] = totals[t].inv();  // ba_invert_totals
+        } else {
+            for (auto& x : totals) x = Fq::zero();  // whatever is left there must not matter to pass B
+            for (auto& x : prefix) x = Fq::zero();
+        }
         for (uint64_t t = 0; t < nthreads; ++t) ba_thread_b(t, L, lv, prefix.data(), totals.data(), pts[l & 1].data());
         lv.entries = nullptr;
         lv.points = pts[l & 1].data();
