@@ -82,3 +82,28 @@ def test_job_fanout_is_balanced_and_complete():
         assert sum(len(p) for p in parts) == len(jobs)
         loads = [sum(j[2] for j in p) for p in parts]
         assert max(loads) <= sum(loads) / world + 44.0  # within one job of perfect balance
+
+
+def test_shard_ranges_partition_and_lpt_balances():
+    """host logic properties: shard_range tiles [0, n) without gaps for every world size; assign_jobs (LPT) places every job
+    once and its makespan is within 4/3 of the trivial lower bound"""
+    import importlib
+    import random
+
+    multi = importlib.import_module("scroll-prover_b200.multi")
+    rng = random.Random(5)
+    for n in (0, 1, 7, 8, 1000, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            ranges = [multi.shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    for trial in range(50):
+        world = rng.choice([1, 2, 4, 8])
+        costs = [rng.choice([11, 18, 44, 16]) * rng.uniform(0.9, 1.1) for _ in range(rng.randrange(1, 80))]
+        plan = multi.assign_jobs(costs, world)
+        assert sorted(i for r in plan for i in r) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in r) for r in plan]
+        lower = max(max(costs), sum(costs) / world)
+        assert max(loads) <= 4 / 3 * lower + 1e-9

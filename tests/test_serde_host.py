@@ -84,3 +84,22 @@ def test_generator_compresses_to_the_known_bytes(lib):
     assert bytes(buf) == (1).to_bytes(32, "little")
     out = np.zeros(8, np.uint64)
     assert lib.serde_host_decompress(bytes(buf), C.c_void_p(out.ctypes.data)) == 1 and np.array_equal(out, g)
+
+
+def test_random_points_round_trip_and_agree_with_the_oracle(lib):
+    """compress / decompress on 200 random curve points (both y parities): identity on the point, same bytes as the oracle's codec"""
+    from oracle import oracle as O
+
+    pts = O.fill_points(200, 0x5E4DE, 4)
+    buf = (C.c_uint8 * 32)()
+    out = np.zeros(8, np.uint64)
+    parities = set()
+    for p in pts:
+        p = np.ascontiguousarray(p)
+        lib.serde_host_compress(C.c_void_p(p.ctypes.data), buf)
+        comp = bytes(buf)
+        assert comp == O.g1_compress(p)
+        parities.add(comp[31] >> 6 & 1)
+        assert lib.serde_host_decompress(comp, C.c_void_p(out.ctypes.data)) == 1
+        assert np.array_equal(out, p)
+    assert parities == {0, 1}
