@@ -17,6 +17,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../include/b200zk.h"
@@ -408,6 +409,15 @@ class GraphEvaluator {
         return ValueSource::Intermediate((uint32_t)calcs_.size() - 1);
     }
     size_t num_calculations() const { return calcs_.size(); }
+    // validation + lowering without a device (b200zk_graph_check): {instructions, on-chip slots}; throws Panic with the reason
+    std::pair<uint32_t, uint32_t> check() const {
+        uint32_t ni = 0, ns = 0;
+        char msg[256];
+        int32_t rc = b200zk_graph_check(calcs_.data(), (uint32_t)calcs_.size(), parts_.data(), (uint32_t)parts_.size(),
+                                        (uint32_t)constants_.size(), (uint32_t)rotations_.size(), &ni, &ns, msg, sizeof msg);
+        if (rc != B200ZK_OK) throw Panic(std::string("GraphEvaluator::check: ") + msg);
+        return {ni, ns};
+    }
 
     // GraphEvaluator::evaluate for every row of the extended domain: values[row] = f(previous = values[row], row)
     void evaluate(DeviceColumn& values, const EvaluationDomain& dom, const std::vector<const DeviceColumn*>& fixed,
