@@ -40,3 +40,24 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = run("--steps", "1", "--warmup", "0", "--k", "10", "--no-cpu-baseline")
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) and not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+def test_step_shape_matches_the_layer1_replay():
+    """The unit list of one step is the degree-24 layer replay of DESIGN.md (d): 28 Lagrange commits + 28 transform chains
+    + 7 coefficient commits + 1 quotient inverse transform; 35 MSMs of which 19 witness-like; every unit lands on one rank."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    jobs = b.make_jobs()
+    kinds = [j[0] for j in jobs]
+    assert kinds.count("lmsm") == 28 and kinds.count("ntt") == 28 and kinds.count("msm") == 7 and kinds.count("icoset") == 1
+    msms = [j for j in jobs if j[0] in ("lmsm", "msm")]
+    assert len(msms) == 35 and sum(1 for j in msms if j[1] == "w") == 19
+    assert "2^24" in b.workload_desc(24) and "wall-sec" in b.metric_name(24)
+    for world in (1, 2, 4, 8):
+        plan = b.assign_jobs(jobs, world)  # per rank: the jobs themselves
+        assert sorted(j for r in plan for j in r) == sorted(jobs)
+        loads = [sum(j[2] for j in r) for r in plan]
+        assert max(loads) <= 1.34 * max(sum(loads) / world, max(j[2] for j in jobs))
