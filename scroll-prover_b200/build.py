@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libb200zk.so")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "g1fft.cu", "quotient.cu", "msm_affine.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", os.path.join("..", "..", "include", "b200zk.h"), "graph.hpp", "graph_exec.cuh", "msm_affine.cuh"]
+HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", os.path.join("..", "..", "include", "b200zk.h"), "graph.hpp", "graph_exec.cuh", "msm_affine.cuh", "msm_affine_kernels.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

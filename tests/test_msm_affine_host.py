@@ -95,3 +95,54 @@ def test_no_entries_at_all(lib):
     bases = O.fill_points(4, 1, 1)
     got, want, _ = run(lib, bases, [[], [], []], 16)
     assert not got.any() and np.array_equal(got, want)
+
+
+# ---- the same pipeline with the REAL kernel source under the CUDA emulation layer (tests/host_emul/cuda_emu.hpp): the
+# offset-scan kernels run as blocks of 256 threads meeting at barriers, the activity flag gates pass A and the inversion
+EMU_SRC = os.path.join(HERE, "host_emul", "msm_affine_emu.cpp")
+EMU_SO = os.path.join(HERE, "host_emul", "libmsm_affine_emu.so")
+EMU_HDRS = HDRS + [os.path.join(HERE, "..", "scroll-prover_b200", "csrc", "msm_affine_kernels.cuh"), os.path.join(HERE, "host_emul", "cuda_emu.hpp")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < max(os.path.getmtime(p) for p in [EMU_SRC] + EMU_HDRS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", EMU_SO, EMU_SRC])
+    return C.CDLL(EMU_SO)
+
+
+def run_emu(emu, lib, bases, buckets, L):
+    entries = np.array([i | (0x80000000 if neg else 0) for b in buckets for i, neg in b] or [0], dtype=np.uint32)
+    offsets = np.zeros(len(buckets) + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum([len(b) for b in buckets])
+    nb, m = len(buckets), int(offsets[-1])
+    bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    got, want = np.zeros((nb, 8), np.uint64), np.zeros((nb, 8), np.uint64)
+    vp = C.c_void_p
+    active = emu.msm_affine_emu(vp(bases.ctypes.data), vp(entries.ctypes.data), vp(offsets.ctypes.data), C.c_uint64(nb), C.c_uint64(max(m, 1)),
+                                C.c_uint32(L), vp(got.ctypes.data))
+    lib.msm_buckets_reference(vp(bases.ctypes.data), vp(entries.ctypes.data), vp(offsets.ctypes.data), C.c_uint64(nb), vp(want.ctypes.data))
+    return got, want, active
+
+
+def test_emulated_kernels_small_mixed_buckets(emu, lib):
+    rng = random.Random(31)
+    bases = O.fill_points(50, 0xE31, 4)
+    sizes = [0, 1, 2, 3, 0, 5, 8, 17, 64, 1, 0, 33, 130, 7]
+    buckets = [[(rng.randrange(50), rng.random() < 0.5) for _ in range(s)] for s in sizes]
+    buckets[3] = [(0, False), (0, False), (0, True)]  # tangent, then cancellation against the copy
+    got, want, active = run_emu(emu, lib, bases, buckets, 16)
+    assert np.array_equal(got, want)
+    assert active == 8  # the largest bucket (130 entries) needs ceil(log2 130) levels; the later ones are skipped by the flag
+
+
+def test_emulated_kernels_many_buckets_span_several_scan_tiles(emu, lib):
+    """5000 buckets (three 2048-bucket scan tiles), mostly empty or tiny, one large: the tile sums / tile offsets / in-tile
+    offsets of the real scan kernels must line every bucket up"""
+    rng = random.Random(32)
+    bases = O.fill_points(40, 0xE32, 4)
+    buckets = [[(rng.randrange(40), rng.random() < 0.4) for _ in range(rng.choice([0, 0, 0, 1, 1, 2, 3]))] for _ in range(5000)]
+    buckets[4321] = [(rng.randrange(40), False) for _ in range(300)]
+    got, want, active = run_emu(emu, lib, bases, buckets, 16)
+    assert np.array_equal(got, want)
+    assert active == 9
