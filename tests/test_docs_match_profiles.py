@@ -4,8 +4,10 @@ import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DESIGN = open(os.path.join(ROOT, "DESIGN.md")).read()
-README = open(os.path.join(ROOT, "README.md")).read()
+
+
+def _doc(name):
+    return open(os.path.join(ROOT, name)).read()
 
 
 def bench(name):
@@ -18,6 +20,7 @@ def jsonl(name):
 
 
 def test_bench_lines_quoted_in_design():
+    DESIGN, README = _doc("DESIGN.md"), _doc("README.md")
     for name, digits in (("bench_r01_v12.json", 3), ("bench_r01_v14.json", 3), ("bench_r01_2gpu_v2.json", 3), ("bench_r01_8gpu_v6.json", 3),
                          ("bench_r01_k25.json", 3), ("bench_r01_k26.json", 3)):
         d = bench(name)
@@ -31,6 +34,7 @@ def test_bench_lines_quoted_in_design():
 
 
 def test_quotient_and_sweep_numbers_quoted_in_design():
+    DESIGN = _doc("DESIGN.md")
     k24 = {r["op"]: r for r in jsonl("quotient_time_r01_k24.jsonl")}
     assert f"{k24['graph_evaluate']['ms_best']:.1f} ms" in DESIGN
     assert f"{k24['permutation_product']['ms_best']:.1f} ms" in DESIGN
