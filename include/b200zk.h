@@ -55,7 +55,8 @@ typedef struct b200zk_srs b200zk_srs;
 
 /* ---- context ------------------------------------------------------------------------------- */
 /* devices/n_devices: CUDA ordinals this context drives; this build drives exactly one per context
- * (n_devices == 1; multi-GPU = one process and one context per GPU). */
+ * (n_devices == 1).  Multi-GPU = one process and one context per GPU; the contexts of a job are joined into one
+ * NCCL communicator with b200zk_ctx_comm_init below (the context owns the communicator). */
 B200ZK_API int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out);
 B200ZK_API int32_t b200zk_ctx_destroy(b200zk_ctx* ctx);
 B200ZK_API const char* b200zk_last_error(const b200zk_ctx* ctx);
@@ -65,6 +66,17 @@ B200ZK_API int32_t b200zk_ctx_set_stream(b200zk_ctx* ctx, void* cuda_stream);
 B200ZK_API int32_t b200zk_ctx_synchronize(b200zk_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 B200ZK_API int32_t b200zk_ctx_launch_count(const b200zk_ctx* ctx, uint64_t* out);
+
+/* ---- multi-GPU: context-owned NCCL communicator ------------------------ */
+/* Rank 0 obtains a 128-byte NCCL unique id and hands it to the other ranks over whatever channel the caller already
+ * has (the prover's RPC, MPI, a shared file ...); every rank then joins with its rank / world size.
+ * world == 1 is allowed (no communicator; the sharded entry points degenerate to the single-GPU ones).
+ * Collective: all ranks must call b200zk_ctx_comm_init, and later the *_sharded entry points, in the same order. */
+B200ZK_API int32_t b200zk_comm_unique_id(void* id128);
+B200ZK_API int32_t b200zk_ctx_comm_init(b200zk_ctx* ctx, const void* id128, int rank, int world);
+B200ZK_API int32_t b200zk_ctx_comm_info(const b200zk_ctx* ctx, int* rank, int* world);
+/* the contiguous slice [first, first + count) of n points that `rank` of `world` owns (sizes differ by <= 1) */
+B200ZK_API int32_t b200zk_shard_range(uint64_t n, int rank, int world, uint64_t* first, uint64_t* count);
 
 /* ---- device buffers (lets a caller keep columns resident between calls) --- */
 B200ZK_API int32_t b200zk_buf_alloc(b200zk_ctx* ctx, uint64_t bytes, void** out_dev);
@@ -93,6 +105,17 @@ B200ZK_API int32_t b200zk_srs_len(const b200zk_srs* srs, uint64_t* out);
 B200ZK_API int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars, uint64_t n, void* out_jacobian96);
 /* same with explicit bases (generic best_multiexp; bases are uploaded for the call) */
 B200ZK_API int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96);
+/* partial MSM over the slice [first, first + n) of the registered bases: sum_{i<n} scalars[i] * srs[first + i]
+ * (precomputed tables are used in place -- a slice of them has the same layout).  Building block of the sharded MSM. */
+B200ZK_API int32_t b200zk_msm_g1_range(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars, uint64_t first, uint64_t n,
+                                       void* out_jacobian96);
+/* best_multiexp over n_total points SHARDED BY POINT RANGE across the ranks of the context's communicator (BASELINE
+ * configs[3]): every rank holds the full SRS handle and passes ONLY its slice of the scalars
+ * (b200zk_shard_range(n_total, rank, world)); it computes the partial sum of its slice, the 96-byte partials are
+ * exchanged with one ncclAllGather on the context stream and summed locally.  Every rank receives the same normalised
+ * point -- the bytes of the single-GPU result. */
+B200ZK_API int32_t b200zk_msm_g1_sharded(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars_slice, uint64_t n_total,
+                                         void* out_jacobian96);
 /* sum of `count` Jacobian points (combining per-GPU partial MSMs after the NCCL all-gather) */
 B200ZK_API int32_t b200zk_g1_sum(b200zk_ctx* ctx, const void* jacobian_points, uint64_t count, void* out_jacobian96);
 /* out[i] = scalars[i] * G1 generator, affine (ParamsKZG::setup's g / g_lagrange generation) */

@@ -73,6 +73,12 @@ def _load():
         "b200zk_srs_len": [vp, C.POINTER(u64)],
         "b200zk_msm_g1": [vp, vp, vp, u64, vp],
         "b200zk_msm_g1_bases": [vp, vp, vp, u64, vp],
+        "b200zk_msm_g1_range": [vp, vp, vp, u64, u64, vp],
+        "b200zk_msm_g1_sharded": [vp, vp, vp, u64, vp],
+        "b200zk_comm_unique_id": [vp],
+        "b200zk_ctx_comm_init": [vp, vp, C.c_int, C.c_int],
+        "b200zk_ctx_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "b200zk_shard_range": [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)],
         "b200zk_g1_sum": [vp, vp, u64, vp],
         "b200zk_g1_generator_mul_batch": [vp, vp, u64, vp],
         "b200zk_fft_g1": [vp, vp, u32, vp],
@@ -121,7 +127,8 @@ def _load():
 ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
-    "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_g1_sum",
+    "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_msm_g1_range", "b200zk_msm_g1_sharded",
+    "b200zk_comm_unique_id", "b200zk_ctx_comm_init", "b200zk_ctx_comm_info", "b200zk_shard_range", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_poly_lincomb", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create", "b200zk_graph_check",
@@ -164,6 +171,22 @@ def fr_to_int(a) -> int:
     return sum(int(x) << (64 * i) for i, x in enumerate(a)) * pow(_R_MONT, -1, R_MOD) % R_MOD
 
 
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().b200zk_comm_unique_id(buf)
+    if rc != OK:
+        raise B200zkError(rc, "b200zk_comm_unique_id failed (NCCL not loadable?)")
+    return buf.raw
+
+
+def shard_range(n: int, rank: int, world: int):
+    first, cnt = C.c_uint64(), C.c_uint64()
+    rc = lib().b200zk_shard_range(n, rank, world, C.byref(first), C.byref(cnt))
+    if rc != OK:
+        raise B200zkError(rc, "b200zk_shard_range: bad arguments")
+    return first.value, cnt.value
+
+
 class Context:
     """One per process per GPU (b200zk_ctx)."""
 
@@ -203,6 +226,32 @@ class Context:
         pd, k1 = _ptr(dev)
         ph, k2 = _ptr(host)
         self._ck(lib().b200zk_buf_upload(self._h, pd, ph, nbytes))
+
+    # ---- multi-GPU: the context owns its NCCL communicator
+    def comm_init(self, unique_id: bytes | None, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._ck(lib().b200zk_ctx_comm_init(self._h, buf, rank, world))
+
+    def comm_init_torch(self, dist):
+        """Joins this context into a communicator spanning an initialised torch.distributed job: rank 0 draws the
+        NCCL unique id, torch broadcasts its 128 bytes (the bootstrap channel), every rank calls b200zk_ctx_comm_init."""
+        import torch
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if world == 1:
+            return self.comm_init(None, 0, 1)
+        backend = dist.get_backend()
+        dev = torch.device("cuda", self.device) if backend == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def comm_info(self):
+        r, w = C.c_int(), C.c_int()
+        self._ck(lib().b200zk_ctx_comm_info(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
 
     def set_overlap(self, on: bool):
         self._ck(lib().b200zk_ctx_set_overlap(self._h, int(on)))
@@ -469,6 +518,21 @@ class Srs:
         out = np.zeros(12, np.uint64)
         p, k = _ptr(scalars)
         self.ctx._ck(lib().b200zk_msm_g1(self.ctx._h, self._h, p, n, out.ctypes.data))
+        return out
+
+    def msm_range(self, scalars, first: int, n: int | None = None) -> np.ndarray:
+        """b200zk_msm_g1_range: sum_i scalars[i] * srs[first + i]."""
+        n = _count(scalars, 32) if n is None else n
+        out = np.zeros(12, np.uint64)
+        p, k = _ptr(scalars)
+        self.ctx._ck(lib().b200zk_msm_g1_range(self.ctx._h, self._h, p, first, n, out.ctypes.data))
+        return out
+
+    def msm_sharded(self, scalars_slice, n_total: int) -> np.ndarray:
+        """b200zk_msm_g1_sharded: collective over the context's communicator; pass this rank's scalar slice."""
+        out = np.zeros(12, np.uint64)
+        p, k = _ptr(scalars_slice)
+        self.ctx._ck(lib().b200zk_msm_g1_sharded(self.ctx._h, self._h, p, n_total, out.ctypes.data))
         return out
 
     def release(self):

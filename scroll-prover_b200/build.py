@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libb200zk.so")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "g1fft.cu", "quotient.cu", "msm_affine.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", os.path.join("..", "..", "include", "b200zk.h"), "graph.hpp", "graph_exec.cuh", "msm_affine.cuh", "msm_affine_kernels.cuh"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "g1fft.cu", "quotient.cu", "comm.cu"]
+HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", os.path.join("..", "..", "include", "b200zk.h"), "graph.hpp", "graph_exec.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         run(cmd)
     return LIB
 

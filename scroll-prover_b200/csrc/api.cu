@@ -55,8 +55,6 @@ int32_t b200zk_ctx_create(const int* devices, int n_devices, b200zk_ctx** out) {
     ctx->own_stream = true;
     if (const char* e = getenv("B200ZK_OVERLAP")) ctx->overlap = atoi(e);
     if (const char* e = getenv("B200ZK_ACC_L")) ctx->msm_acc_l = (uint32_t)atoi(e);
-    if (const char* e = getenv("B200ZK_MSM_AFFINE")) ctx->msm_affine = atoi(e);  // experiment knob, default off
-    if (const char* e = getenv("B200ZK_AFFINE_L")) ctx->msm_affine_l = (uint32_t)atoi(e);
     if (const char* e = getenv("B200ZK_SCATTER_SWEEPS")) ctx->msm_scatter_sweeps = (uint32_t)atoi(e);  // experiment knob
     if (cudaMalloc(&ctx->msm_adds_dev, 8) == cudaSuccess) cudaMemset(ctx->msm_adds_dev, 0, 8);
     else ctx->msm_adds_dev = nullptr;
@@ -68,7 +66,8 @@ int32_t b200zk_ctx_destroy(b200zk_ctx* ctx) {
     CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (Scratch* s : {&ctx->ntt_work, &ctx->stage_in, &ctx->stage_out, &ctx->msm_work, &ctx->misc, &ctx->msm_affine_work})
+    comm_destroy(ctx);
+    for (Scratch* s : {&ctx->ntt_work, &ctx->stage_in, &ctx->stage_out, &ctx->msm_work, &ctx->misc})
         if (s->p) cudaFree(s->p);
     for (auto& t : ctx->tables) cudaFree(t.dev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

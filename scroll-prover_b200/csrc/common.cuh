@@ -57,7 +57,6 @@ struct b200zk_ctx {
     int sm_count = 148;
     // scratch pools
     b200zk::Scratch ntt_work, stage_in, stage_out, msm_work, misc;
-    b200zk::Scratch msm_affine_work;  // point / prefix arrays of the experimental batched-affine accumulation (msm_affine.cu)
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<b200zk::TwiddleTable> tables;
@@ -78,12 +77,17 @@ struct b200zk_ctx {
     uint32_t msm_window = 0;
     uint32_t msm_scatter_sweeps = 0;
     uint32_t msm_acc_l = 0;
-    uint32_t msm_affine_l = 0;  // output slots per thread of the batched-affine levels (0 = default)
-    int msm_affine = 0;      // 1: batched-affine bucket accumulation (experimental, B200ZK_MSM_AFFINE); 0: XYZZ lock-step chunks
     int srs_precompute = 1;  // 1 auto: SRS handles of >= 2^16 points keep 2^(c*w) multiples when memory allows
     unsigned long long* msm_adds_dev = nullptr;  // running count of bucket additions actually performed
     uint32_t last_c = 0, last_windows = 0;
     uint64_t last_adds = 0;
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE opt-in: the "already done" flags live in the
+    // context (one device per context), not in process-wide statics
+    uint32_t smem_optin = 0;
+    // multi-GPU (comm.cu): the context owns its NCCL communicator
+    void* nccl_comm = nullptr;   // ncclComm_t
+    void* comm_buf = nullptr;    // (world + 1) x 96 B: gathered partial points + this rank's own
+    int comm_rank = 0, comm_world = 1;  // bit i: kernel family i has its opt-in on this context's device
 };
 
 namespace b200zk {
@@ -246,6 +250,7 @@ inline int32_t deliver(b200zk_ctx* ctx, void* dst, const void* dev_src, size_t b
 // implemented in ntt.cu / msm.cu / poly.cu
 int32_t ntt_get_table(b200zk_ctx* ctx, const Fr& omega, uint32_t log_n, const Fr** out);
 Fr host_zeta();
+int32_t comm_destroy(b200zk_ctx* ctx);  // comm.cu
 int32_t ntt_run(b200zk_ctx* ctx, const Fr* in, uint32_t log_in, Fr* out, uint32_t log_n, const Fr& omega,
                 int inverse_scale, int coset_mode);
 

@@ -503,9 +503,6 @@ static uint32_t pick_window(uint64_t n) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int32_t msm_affine_accumulate(b200zk_ctx* ctx, const Affine* bases, const uint32_t* entries, const uint32_t* offsets, uint64_t NB,
-                              uint64_t max_entries, XYZZ* buckets);  // msm_affine.cu
-
 // out[i] = 2^c * in[i] (affine): one table of the precomputed SRS from the previous one
 __global__ void __launch_bounds__(128) srs_shift_kernel(const Affine* __restrict__ in, Affine* __restrict__ out, uint64_t n, uint32_t c) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -645,10 +642,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         }
         B2_LAUNCH_CHECK(ctx);
         uint32_t ablocks = (uint32_t)((nthreads + 255) / 256);
-        if (ctx->msm_affine) {  // experimental: pairwise batched-affine tree instead of accumulate + combine (msm_affine.cu)
-            ProfScope ps_(ctx, PROF_MSM_ACCUM);
-            B2_TRY(msm_affine_accumulate(ctx, bases, entries, offsets, pl.NB, max_entries, buckets));
-        } else {
         {
             ProfScope ps_(ctx, PROF_MSM_ACCUM);
             msm_accumulate<<<ablocks, 256, 0, st>>>(bases, entries, offsets, pl.NB, buckets, pid, pval, nthreads, giant_flag, ACC_L);
@@ -672,7 +665,6 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             msm_combine_final<<<(uint32_t)((nrec + 127) / 128), 128, 0, st>>>(in_id, in_val, nrec, buckets, giant_flag);
             B2_LAUNCH_CHECK(ctx);
         }
-        }  // !msm_affine
     }
     {
         ProfScope ps_(ctx, PROF_MSM_REDUCE);

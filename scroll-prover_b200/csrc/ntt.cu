@@ -368,11 +368,11 @@ static int32_t launch_pass(b200zk_ctx* ctx, const Fr* in, Fr* out, const Fr* tab
                            const Fr3& post_c) {
     uint32_t L = 1u << ps.m, E = L * C;
     size_t smem = (size_t)(2 * E + (LAST ? 0 : 2 * L)) * sizeof(uint4);
-    static bool attr_set = false;
-    if (!attr_set) {
+    const uint32_t optin_bit = 1u << ((C == 8 ? 0 : 2) + (LAST ? 1 : 0));
+    if (!(ctx->smem_optin & optin_bit)) {
         B2_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<C, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)((2 * (1u << NTT_MAX_DIGIT) * C + 2 * (1u << NTT_MAX_DIGIT)) * sizeof(uint4))));
-        attr_set = true;
+        ctx->smem_optin |= optin_bit;
     }
     uint64_t tiles = (1ull << ps.log_n) / E;
     uint32_t nb = (L >> 2) * C;  // radix-4 groups per double stage

@@ -138,10 +138,9 @@ static uint32_t graph_block_rows(uint32_t n_slots, size_t* smem_bytes) {
 int32_t graph_evaluate_run(b200zk_ctx* ctx, const b200zk_graph* g, GraphLaunch L) {
     size_t smem = 0;
     uint32_t T = graph_block_rows(g->prog.n_slots, &smem);
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) {
+    if (!(ctx->smem_optin & (1u << 8))) {
         B2_CUDA(ctx, cudaFuncSetAttribute(graph_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
-        attr_bytes = 224 * 1024;
+        ctx->smem_optin |= 1u << 8;
     }
     uint64_t size = 1ull << L.log_size;
     uint32_t blocks = (uint32_t)((size + T - 1) / T);
