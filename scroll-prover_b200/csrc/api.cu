@@ -10,6 +10,9 @@
 namespace b200zk {
 int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev, uint32_t pre_c,
                 uint64_t pre_stride);
+int32_t msm_run_batch(b200zk_ctx* ctx, const Affine* bases, const Fr* const* cols, uint32_t batch, uint64_t n, Jacobian* out_dev,
+                      uint32_t pre_c, uint64_t pre_stride);
+uint32_t msm_max_batch(uint64_t n, uint32_t pre_c);
 uint32_t msm_pick_window_precomputed(uint64_t n);
 int32_t srs_precompute_run(b200zk_ctx* ctx, Affine* tables, uint64_t n, uint32_t c, uint32_t W);
 int32_t g1_sum_run(b200zk_ctx* ctx, const Jacobian* pts, uint64_t count, Jacobian* out_dev);
@@ -381,7 +384,10 @@ static int32_t pipeline_init(b200zk_ctx* ctx) {
 }
 
 // One call = a list of independent per-column jobs of plonk::create_proof whose inputs are in HOST memory (pinned for
-// overlap): the H2D copy of job j+1 runs on a copy stream while job j computes; no host synchronisation inside the loop.
+// overlap) or already on the device.  Jobs are taken in GROUPS: a group is uploaded (copy stream) while the previous one
+// computes, and the commitments of a group's consecutive jobs over the same SRS go through ONE batched MSM pipeline
+// (msm_run_batch) -- for 2^20-row columns that is up to 16 columns per pipeline, a 2^24+ column is a group of its own.
+// No host synchronisation inside the loop.
 int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k, const void* omega_inv32,
                                const void* extended_omega32, const void* extended_omega_inv32, uint32_t extended_k,
                                void* commits_out) {
@@ -391,14 +397,14 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
     bool any_commit = false, any_coeff = false, any_ext = false, any_quot = false;
     for (uint32_t j = 0; j < count; ++j) {
         const b200zk_column_job& jb = jobs[j];
-        if (!jb.host_values || jb.mode < 0 || jb.mode > 4) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: job %u malformed", j);
+        if (!jb.host_values || jb.mode < 0 || jb.mode > 5) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: job %u malformed", j);
         if (jb.mode <= 2) {
             if (!jb.srs || jb.srs->ctx != ctx || n > jb.srs->n)
                 return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: job %u needs an SRS of this context with >= 2^k bases", j);
             any_commit = true;
         }
         any_coeff |= (jb.mode >= 1 && jb.mode <= 3);
-        any_ext |= (jb.mode == 2 || jb.mode == 3);
+        any_ext |= (jb.mode == 2 || jb.mode == 3 || jb.mode == 5);
         any_quot |= (jb.mode == 4);
     }
     if (any_commit && !commits_out) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: commits_out is null");
@@ -413,7 +419,40 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
     if (any_ext) B2_TRY(read_fr(ctx, extended_omega32, &ext_omega));
     if (any_quot) B2_TRY(read_fr(ctx, extended_omega_inv32, &ext_omega_inv));
     const size_t col_bytes = sizeof(Fr) * n, ext_bytes = sizeof(Fr) << extended_k;
-    for (int i = 0; i < 2; ++i) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], any_quot ? ext_bytes : col_bytes));
+
+    // ---- groups: [first, first + len); a mode-4 job (2^extended_k input values) is always a group of its own
+    auto pre_of = [&](const b200zk_srs* s) -> uint32_t { return (n * 16 >= s->n) ? s->pre_c : 0; };
+    uint32_t gmax = 1;
+    for (uint32_t j = 0; j < count; ++j)
+        if (jobs[j].mode <= 2) {
+            gmax = msm_max_batch(n, pre_of(jobs[j].srs));
+            break;
+        }
+    if (gmax > 16) gmax = 16;
+    struct Group { uint32_t first, len; };
+    std::vector<Group> groups;
+    std::vector<uint8_t> is_dev(count);
+    for (uint32_t j = 0; j < count; ++j) is_dev[j] = is_device_ptr(jobs[j].host_values) ? 1 : 0;
+    for (uint32_t j = 0; j < count;) {
+        if (jobs[j].mode == 4) {
+            groups.push_back({j, 1});
+            ++j;
+            continue;
+        }
+        uint32_t len = 0;
+        while (j + len < count && len < gmax && jobs[j + len].mode != 4) ++len;
+        groups.push_back({j, len});
+        j += len;
+    }
+    size_t stage_bytes = 0;  // host inputs of the largest group
+    for (const Group& gr : groups) {
+        size_t b = 0;
+        for (uint32_t j = gr.first; j < gr.first + gr.len; ++j)
+            if (!is_dev[j]) b += (jobs[j].mode == 4) ? ext_bytes : col_bytes;
+        if (b > stage_bytes) stage_bytes = b;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (stage_bytes) B2_TRY(scratch_reserve(ctx, ctx->colstage[i], stage_bytes));
     B2_TRY(scratch_reserve(ctx, ctx->col_commits, sizeof(Jacobian) * count));
     if (any_coeff) B2_TRY(scratch_reserve(ctx, ctx->col_coeff, col_bytes));
     if (any_ext || any_quot) B2_TRY(scratch_reserve(ctx, ctx->col_ext, ext_bytes));
@@ -423,7 +462,7 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
     // Two compute streams: the commitments (MSM) run on the context stream, the transforms of the same column on
     // aux_stream.  Only msm_accumulate and the NTT passes are bound by the INT32 pipe; the MSM's sort / reduction phases
     // are latency- or memory-bound and overlap with the other stream's butterflies.
-    const bool overlap = ctx->overlap && (any_coeff || any_quot) && any_commit;
+    const bool overlap = ctx->overlap && (any_coeff || any_quot || any_ext) && any_commit;
     cudaStream_t main_stream = ctx->stream, ntt_stream = overlap ? ctx->aux_stream : ctx->stream;
     struct StreamSwap {  // ntt_run / msm_run launch on ctx->stream
         b200zk_ctx* c;
@@ -449,49 +488,87 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
     if (overlap) B2_CUDA(ctx, cudaStreamWaitEvent(ntt_stream, ctx->ev_fork, 0));
 
     bool used_main[2] = {false, false}, used_aux[2] = {false, false};
-    auto is_dev = [&](uint32_t j) { return is_device_ptr(jobs[j].host_values); };
-    auto upload = [&](uint32_t j) -> int32_t {
-        if (is_dev(j)) return B200ZK_OK;  // already resident: used in place
-        int b = j & 1;
-        if (used_main[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
-        if (used_aux[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used_aux[b], 0));
-        B2_CUDA(ctx, cudaMemcpyAsync(ctx->colstage[b].p, jobs[j].host_values, jobs[j].mode == 4 ? ext_bytes : col_bytes,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-        B2_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    std::vector<const Fr*> src(count);  // device address of every job's input
+    bool any_host_copy = false;
+    auto upload = [&](uint32_t gi) -> int32_t {  // returns with ev_copied[gi & 1] recorded when the group has host inputs
+        const Group& gr = groups[gi];
+        const int b = gi & 1;
+        size_t off = 0;
+        bool first_copy = true;
+        for (uint32_t j = gr.first; j < gr.first + gr.len; ++j) {
+            if (is_dev[j]) {
+                src[j] = (const Fr*)jobs[j].host_values;  // already resident: used in place
+                continue;
+            }
+            if (first_copy) {
+                if (used_main[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));
+                if (used_aux[b]) B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used_aux[b], 0));
+                first_copy = false;
+            }
+            size_t bytes = (jobs[j].mode == 4) ? ext_bytes : col_bytes;
+            char* dst = (char*)ctx->colstage[b].p + off;
+            B2_CUDA(ctx, cudaMemcpyAsync(dst, jobs[j].host_values, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            src[j] = (const Fr*)dst;
+            off += bytes;
+        }
+        if (!first_copy) {
+            B2_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            any_host_copy = true;
+        }
         return B200ZK_OK;
     };
     B2_TRY(upload(0));
-    for (uint32_t j = 0; j < count; ++j) {
-        const b200zk_column_job& jb = jobs[j];
-        const int b = j & 1;
-        const bool dev_in = is_dev(j);
-        if (j + 1 < count) B2_TRY(upload(j + 1));
-        const Fr* col = dev_in ? (const Fr*)jb.host_values : (const Fr*)ctx->colstage[b].p;
-        const bool has_msm = jb.mode <= 2, has_ntt = jb.mode >= 1;
-        if (has_msm) {
-            if (!dev_in) B2_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_copied[b], 0));
-            B2_TRY(msm_run(ctx, (const Affine*)jb.srs->dev_bases, col, n, commits + j, (n * 16 >= jb.srs->n) ? jb.srs->pre_c : 0,
-                           jb.srs->n));
-            if (!dev_in) {
+    for (uint32_t gi = 0; gi < groups.size(); ++gi) {
+        const Group& gr = groups[gi];
+        const int b = gi & 1;
+        if (gi + 1 < groups.size()) B2_TRY(upload(gi + 1));
+        bool host_in = false, grp_msm = false, grp_ntt = false;
+        for (uint32_t j = gr.first; j < gr.first + gr.len; ++j) {
+            host_in |= !is_dev[j];
+            grp_msm |= jobs[j].mode <= 2;
+            grp_ntt |= jobs[j].mode >= 1;
+        }
+        if (grp_msm) {
+            if (host_in) B2_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_copied[b], 0));
+            for (uint32_t j = gr.first; j < gr.first + gr.len;) {  // runs of consecutive commitments over the same SRS
+                if (jobs[j].mode > 2) {
+                    ++j;
+                    continue;
+                }
+                const b200zk_srs* srs = jobs[j].srs;
+                const uint32_t pre_c = pre_of(srs), bmax = msm_max_batch(n, pre_c);
+                uint32_t len = 1;
+                while (j + len < gr.first + gr.len && len < bmax && jobs[j + len].mode <= 2 && jobs[j + len].srs == srs) ++len;
+                B2_TRY(msm_run_batch(ctx, (const Affine*)srs->dev_bases, &src[j], len, n, commits + j, pre_c, srs->n));
+                j += len;
+            }
+            if (host_in) {
                 B2_CUDA(ctx, cudaEventRecord(ctx->ev_used[b], main_stream));
                 used_main[b] = true;
             }
         }
-        if (has_ntt) {
+        if (grp_ntt) {
             StreamSwap sw(ctx, ntt_stream);
-            if (!dev_in) B2_CUDA(ctx, cudaStreamWaitEvent(ntt_stream, ctx->ev_copied[b], 0));
-            if (jb.mode <= 3) {
-                Fr* coeff = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_coeff.p;
-                B2_TRY(ntt_run(ctx, col, k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
-                if (jb.mode >= 2) {
+            if (host_in) B2_CUDA(ctx, cudaStreamWaitEvent(ntt_stream, ctx->ev_copied[b], 0));
+            for (uint32_t j = gr.first; j < gr.first + gr.len; ++j) {
+                const b200zk_column_job& jb = jobs[j];
+                if (jb.mode < 1) continue;
+                if (jb.mode <= 3) {
+                    Fr* coeff = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_coeff.p;
+                    B2_TRY(ntt_run(ctx, src[j], k, coeff, k, omega_inv, 1, B200ZK_COSET_NONE));
+                    if (jb.mode >= 2) {
+                        Fr* ext = jb.ext_out_dev ? (Fr*)jb.ext_out_dev : (Fr*)ctx->col_ext.p;
+                        B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
+                    }
+                } else if (jb.mode == 4) {
+                    Fr* out = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_ext.p;
+                    B2_TRY(ntt_run(ctx, src[j], extended_k, out, extended_k, ext_omega_inv, 1, B200ZK_COSET_POST));
+                } else {  // mode 5: coefficients -> extended coset
                     Fr* ext = jb.ext_out_dev ? (Fr*)jb.ext_out_dev : (Fr*)ctx->col_ext.p;
-                    B2_TRY(ntt_run(ctx, coeff, k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
+                    B2_TRY(ntt_run(ctx, src[j], k, ext, extended_k, ext_omega, 0, B200ZK_COSET_PRE));
                 }
-            } else {
-                Fr* out = jb.coeff_out_dev ? (Fr*)jb.coeff_out_dev : (Fr*)ctx->col_ext.p;
-                B2_TRY(ntt_run(ctx, col, extended_k, out, extended_k, ext_omega_inv, 1, B200ZK_COSET_POST));
             }
-            if (!dev_in) {
+            if (host_in) {
                 B2_CUDA(ctx, cudaEventRecord(overlap ? ctx->ev_used_aux[b] : ctx->ev_used[b], ntt_stream));
                 (overlap ? used_aux : used_main)[b] = true;
             }
@@ -501,7 +578,11 @@ int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, u
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_join, ntt_stream));
         B2_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
     }
-    if (!any_commit) return B200ZK_OK;
+    if (!any_commit) {
+        // no result to read back: still make sure every H2D copy has left the caller's host buffers before returning
+        if (any_host_copy) B2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        return B200ZK_OK;
+    }
     return deliver(ctx, commits_out, commits, sizeof(Jacobian) * count);
 }
 

@@ -29,13 +29,23 @@ static constexpr uint32_t PART_INVALID = 0x1fffffffu;  // also the bucket-id mas
 static constexpr uint32_t PART_GIANT = 0x20000000u;
 static constexpr uint32_t PART_STARTS = 0x80000000u;
 static constexpr uint32_t PART_ENDS = 0x40000000u;
+static constexpr int MSM_MAX_BATCH = 32;
 static constexpr int ACC_L_DEFAULT = 256;  // sorted entries per accumulate thread (B200ZK_ACC_L overrides, experiments)
 
 struct MsmPlan {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
-    uint32_t Ws;        // bucket sets: W, or 1 when the SRS holds precomputed 2^(c*w) multiples of every base
+    uint32_t Ws;        // bucket sets per column: W, or 1 when the SRS holds precomputed 2^(c*w) multiples of every base
+    uint32_t batch;     // columns (scalar vectors over the SAME bases) summed in one pipeline; bucket set = col * Ws + w
     uint64_t stride;    // precomputed SRS: table w starts at bases + w*stride (0 otherwise)
-    uint64_t NB;        // Ws * B
+    uint64_t NB;        // batch * Ws * B
+};
+
+// Batched MSM: up to MSM_MAX_BATCH columns over the same bases go through ONE count / sort / accumulate / reduce pipeline
+// (their bucket sets lie side by side), so the latency-bound phases -- scans, the bucket reduction, the final Horner --
+// are paid once per batch instead of once per column.  This is what the hundreds of 2^20-row columns of the inner
+// (zkEVM super-circuit) proof need; a 2^24+ column fills the machine alone and runs with batch = 1.
+struct MsmCols {
+    const Fr* p[MSM_MAX_BATCH];
 };
 
 __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
@@ -48,9 +58,18 @@ __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
 }
 
 // every scalar once: canonical form, signed digits -> digits[w*n + i] (magnitude | sign<<31, 0 = skip) + histogram
-__global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, MsmPlan pl, uint32_t* hist, uint32_t* digits) {
+__global__ void __launch_bounds__(256) msm_count(MsmCols cols, uint64_t n, MsmPlan pl, uint32_t* hist, uint32_t* digits_all) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t total = n * pl.batch;
+    for (uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
+        const uint32_t col = (uint32_t)(gi / n);
+        const uint64_t i = gi - (uint64_t)col * n;
+        const Fr* scalars = cols.p[0];
+#pragma unroll
+        for (int q = 1; q < MSM_MAX_BATCH; ++q)
+            if (q == (int)col) scalars = cols.p[q];  // no dynamic indexing of kernel parameters
+        uint32_t* digits = digits_all + (uint64_t)col * pl.W * n;
+        uint32_t* hist_c = hist + (uint64_t)col * pl.Ws * pl.B;
         Fr s = scalars[i];
         if (s.is_zero()) {
             for (uint32_t w = 0; w < pl.W; ++w) digits[(uint64_t)w * n + i] = 0;
@@ -77,7 +96,7 @@ __global__ void __launch_bounds__(256) msm_count(const Fr* scalars, uint64_t n, 
                 carry = 0;
             }
             digits[(uint64_t)w * n + i] = enc;
-            if (enc) atomicAdd(&hist[(pl.Ws == 1 ? 0ull : (uint64_t)w * pl.B) + (enc & 0x7fffffffu) - 1], 1u);
+            if (enc) atomicAdd(&hist_c[(pl.Ws == 1 ? 0ull : (uint64_t)w * pl.B) + (enc & 0x7fffffffu) - 1], 1u);
         }
     }
 }
@@ -100,16 +119,17 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
     }
     if (sweep >= eff) return;
     const uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sweep / eff), b_hi = (uint32_t)((uint64_t)pl.B * (sweep + 1) / eff);
-    uint64_t total = n * pl.W;
+    uint64_t total = n * pl.W * pl.batch;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         uint32_t d = digits[idx];
         if (!d) continue;
         uint32_t bk = (d & 0x7fffffffu) - 1;
         if (bk < b_lo || bk >= b_hi) continue;
-        uint64_t w = idx / n;
-        uint32_t i = (uint32_t)(idx - w * n);
-        uint32_t pos = atomicAdd(&cursor[(pl.Ws == 1 ? 0ull : w * pl.B) + (d & 0x7fffffffu) - 1], 1u);
+        uint64_t cw = idx / n;  // col * W + w
+        uint32_t i = (uint32_t)(idx - cw * n);
+        uint64_t col = cw / pl.W, w = cw - col * pl.W;
+        uint32_t pos = atomicAdd(&cursor[(col * pl.Ws + (pl.Ws == 1 ? 0ull : w)) * pl.B + bk], 1u);
         entries[pos] = (uint32_t)(i + w * pl.stride) | (d & 0x80000000u);
     }
 }
@@ -155,16 +175,21 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_tile_sums(const uint32_t* in, u
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
-__global__ void scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total, unsigned long long* running) {
-    if (threadIdx.x || blockIdx.x) return;
-    uint32_t acc = 0;
-    for (uint32_t i = 0; i < ntiles; ++i) {
-        uint32_t v = tile_sums[i];
-        tile_sums[i] = acc;
-        acc += v;
+// one block: exclusive scan of the tile sums in chunks of SCAN_TPB with a running carry
+__global__ void __launch_bounds__(SCAN_TPB) scan_tile_offsets(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total,
+                                                              unsigned long long* running) {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += SCAN_TPB) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
     }
-    *grand_total = acc;
-    if (running) atomicAdd(running, (unsigned long long)acc);
+    if (threadIdx.x == 0) {
+        *grand_total = carry;
+        if (running) atomicAdd(running, (unsigned long long)carry);
+    }
 }
 __global__ void __launch_bounds__(SCAN_TPB) scan_apply(const uint32_t* in, uint64_t n, const uint32_t* tile_offs, uint32_t* out,
                                                      uint32_t* out2) {
@@ -444,8 +469,10 @@ __global__ void __launch_bounds__(512) msm_weighted_sums(XYZZ* __restrict__ vec,
     }
 }
 
-__global__ void msm_finish(MsmPlan pl, uint32_t kc, const XYZZ* __restrict__ sums, Jacobian* out) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void msm_finish(MsmPlan pl, uint32_t kc, const XYZZ* __restrict__ sums_all, Jacobian* out_all) {
+    if (threadIdx.x) return;
+    const XYZZ* sums = sums_all + (uint64_t)blockIdx.x * pl.Ws * 3;  // block = column of the batch
+    Jacobian* out = out_all + blockIdx.x;
     XYZZ acc = XYZZ::identity();
     for (uint32_t w = pl.Ws; w-- > 0;) {
         for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);   // no-op while acc is the identity (Ws == 1)
@@ -539,23 +566,36 @@ int32_t srs_precompute_run(b200zk_ctx* ctx, Affine* tables, uint64_t n, uint32_t
     return B200ZK_OK;
 }
 
-// pre_c != 0: `bases` is a precomputed SRS (W tables of stride pre_stride) built for window pre_c
-int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev, uint32_t pre_c,
-                uint64_t pre_stride) {
+// how many columns of n scalars one batched pipeline may take (sorted-entry positions are 32-bit; scratch stays ~2 GiB)
+uint32_t msm_max_batch(uint64_t n, uint32_t pre_c) {
+    uint32_t c = pre_c ? pre_c : pick_window(n);
+    uint64_t per_col = (n ? n : 1) * (254 / c + 1);
+    uint64_t b = (1ull << 28) / per_col;
+    return (uint32_t)(b < 1 ? 1 : (b > MSM_MAX_BATCH ? MSM_MAX_BATCH : b));
+}
+
+// pre_c != 0: `bases` is a precomputed SRS (W tables of stride pre_stride) built for window pre_c.
+// cols[0 .. batch): device pointers of `batch` scalar vectors of n elements each; out_dev[0 .. batch).
+int32_t msm_run_batch(b200zk_ctx* ctx, const Affine* bases, const Fr* const* cols, uint32_t batch, uint64_t n, Jacobian* out_dev,
+                      uint32_t pre_c, uint64_t pre_stride) {
     if (n >= (1ull << 31)) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n = %llu >= 2^31", (unsigned long long)n);
+    if (batch < 1 || batch > (uint32_t)MSM_MAX_BATCH) return fail(ctx, B200ZK_E_INVALID, "msm: batch %u out of range [1,%d]", batch, MSM_MAX_BATCH);
     MsmPlan pl;
     pl.c = pre_c ? pre_c : (ctx->msm_window ? ctx->msm_window : pick_window(n));
     if (pl.c < 2 || pl.c > 24) return fail(ctx, B200ZK_E_INVALID, "msm: window %u out of range [2,24]", pl.c);
     pl.W = 254 / pl.c + 1;
     pl.B = 1u << (pl.c - 1);
     pl.Ws = pre_c ? 1 : pl.W;
+    pl.batch = batch;
     pl.stride = pre_c ? pre_stride : 0;
-    pl.NB = (uint64_t)pl.Ws * pl.B;
-    uint64_t max_entries = n * pl.W;
-    if (max_entries >= 0xffffffffull) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n*W too large for window %u", pl.c);
+    pl.NB = (uint64_t)batch * pl.Ws * pl.B;
+    uint64_t max_entries = n * pl.W * batch;
+    if (max_entries >= 0xffffffffull) return fail(ctx, B200ZK_E_UNSUPPORTED, "msm: n*W*batch too large for window %u", pl.c);
+    MsmCols colp;
+    for (int q = 0; q < MSM_MAX_BATCH; ++q) colp.p[q] = cols[q < (int)batch ? q : 0];
     ctx->last_c = pl.c;
     ctx->last_windows = pl.W;
-    ctx->last_adds = max_entries;
+    ctx->last_adds = n * pl.W;
 
     const uint32_t ACC_L = ctx->msm_acc_l ? ctx->msm_acc_l : (uint32_t)ACC_L_DEFAULT;
     uint64_t nthreads = (max_entries + ACC_L - 1) / ACC_L;
@@ -575,8 +615,9 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     size_t o_pid2 = carve(4 * 2 * nthreads2), o_pval2 = carve(sizeof(XYZZ) * 2 * nthreads2);
     const uint32_t kc = pl.c / 2;                       // columns = 2^kc, rows = B / 2^kc  (c - 1 = kc + kr)
     const uint32_t red_cols = 1u << kc, red_rows = pl.B >> kc;
-    size_t red_len = (size_t)pl.Ws * (red_rows + red_cols);
-    size_t o_gr = carve(sizeof(XYZZ) * red_len), o_gw = carve(sizeof(XYZZ) * red_len), o_sums = carve(sizeof(XYZZ) * 3 * pl.Ws);
+    const uint32_t sets = batch * pl.Ws;
+    size_t red_len = (size_t)sets * (red_rows + red_cols);
+    size_t o_gr = carve(sizeof(XYZZ) * red_len), o_gw = carve(sizeof(XYZZ) * red_len), o_sums = carve(sizeof(XYZZ) * 3 * sets);
     B2_TRY(scratch_reserve(ctx, ctx->msm_work, off));
     char* base = (char*)ctx->msm_work.p;
     uint32_t* hist = (uint32_t*)(base + o_hist);
@@ -601,11 +642,11 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     B2_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * pl.NB, st));
     uint32_t sblocks = (uint32_t)ctx->sm_count * 8;
     if (n) {
-        uint64_t want = (n + 255) / 256;
+        uint64_t want = (n * batch + 255) / 256;
         uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
         {
             ProfScope ps_(ctx, PROF_MSM_COUNT);
-            msm_count<<<blocks, 256, 0, st>>>(scalars, n, pl, hist, digits);
+            msm_count<<<blocks, 256, 0, st>>>(colp, n, pl, hist, digits);
         }
         B2_LAUNCH_CHECK(ctx);
     }
@@ -613,7 +654,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
         ProfScope ps_(ctx, PROF_MSM_SCAN);
         scan_tile_sums<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles);
         B2_LAUNCH_CHECK(ctx);
-        scan_tile_offsets<<<1, 32, 0, st>>>(tiles, ntiles, offsets + pl.NB, ctx->msm_adds_dev);
+        scan_tile_offsets<<<1, SCAN_TPB, 0, st>>>(tiles, ntiles, offsets + pl.NB, ctx->msm_adds_dev);
         B2_LAUNCH_CHECK(ctx);
         scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(hist, pl.NB, tiles, offsets, cursor);
         B2_LAUNCH_CHECK(ctx);
@@ -625,7 +666,7 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
             {
                 uint32_t sweeps = 1;
-                if (pl.Ws == 1) {
+                if (pl.Ws == 1 && batch == 1) {
                     // measured on B200 at n = 2^24 (805 MB of entries): 1 sweep 6.3 ms, 2: 4.9, 4: 4.1, 16: 11.5 -- each
                     // sweep re-reads the digits, so only a few sweeps of ~200 MB pay off
                     uint64_t region = 200ull << 20;
@@ -668,14 +709,19 @@ int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_
     }
     {
         ProfScope ps_(ctx, PROF_MSM_REDUCE);
-        msm_rowcol_sums<<<dim3(red_rows + red_cols, pl.Ws), RED_T, 0, st>>>(buckets, pl.B, kc, grpR);
+        msm_rowcol_sums<<<dim3(red_rows + red_cols, sets), RED_T, 0, st>>>(buckets, pl.B, kc, grpR);
         B2_LAUNCH_CHECK(ctx);
-        msm_weighted_sums<<<dim3(2, pl.Ws), 512, 0, st>>>(grpR, grpW, pl.B, kc, red_sums);
+        msm_weighted_sums<<<dim3(2, sets), 512, 0, st>>>(grpR, grpW, pl.B, kc, red_sums);
         B2_LAUNCH_CHECK(ctx);
-        msm_finish<<<1, 32, 0, st>>>(pl, kc, red_sums, out_dev);
+        msm_finish<<<batch, 32, 0, st>>>(pl, kc, red_sums, out_dev);
         B2_LAUNCH_CHECK(ctx);
     }
     return B200ZK_OK;
+}
+
+int32_t msm_run(b200zk_ctx* ctx, const Affine* bases, const Fr* scalars, uint64_t n, Jacobian* out_dev, uint32_t pre_c,
+                uint64_t pre_stride) {
+    return msm_run_batch(ctx, bases, &scalars, 1, n, out_dev, pre_c, pre_stride);
 }
 
 int32_t g1_sum_run(b200zk_ctx* ctx, const Jacobian* pts, uint64_t count, Jacobian* out_dev) {

@@ -107,3 +107,24 @@ def test_shard_ranges_partition_and_lpt_balances():
         loads = [sum(costs[i] for i in r) for r in plan]
         lower = max(max(costs), sum(costs) / world)
         assert max(loads) <= 4 / 3 * lower + 1e-9
+
+
+def test_abi_shard_range_tiles_the_points_and_matches_the_host_helper():
+    """b200zk_shard_range (no device needed) is the partition b200zk_msm_g1_sharded uses: contiguous, covering,
+    sizes differing by at most one, identical to multi.shard_range."""
+    import importlib
+
+    zk = importlib.import_module("scroll-prover_b200")
+    multi = importlib.import_module("scroll-prover_b200.multi")
+    for n in (0, 1, 5, 8, 1000, (1 << 17) + 3, 1 << 26):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            sizes = []
+            for r in range(world):
+                first, cnt = zk.shard_range(n, r, world)
+                assert first == nxt and (first, first + cnt) == multi.shard_range(n, r, world)
+                nxt += cnt
+                sizes.append(cnt)
+            assert nxt == n and max(sizes) - min(sizes) <= 1
+    with pytest.raises(zk.B200zkError):
+        zk.shard_range(10, 3, 3)

@@ -1,9 +1,9 @@
 """SURVEY.md §8(d) config 4 / BASELINE configs[3]: one MSM of 2^20 .. 2^26 points sharded by point range over N GPUs.
 
-One process per GPU (torchrun); rank r keeps bases[lo_r:hi_r] resident (generated on the device: [s_i]G), computes a
-full local Pippenger over its slice of the scalars, the 96-byte partial points are all-gathered over NCCL and summed with
-b200zk_g1_sum (scroll-prover_b200/multi.py).  Timed on the device (CUDA events around the local MSM + gather + sum, MAX over
-ranks), uniform and witness-like scalars.  Prints one JSON line per size on rank 0.
+One process per GPU (torchrun); every rank holds the full SRS handle (generated on the device: [s_i]G, precomputed tables
+when they fit) and calls b200zk_msm_g1_sharded with its slice of the scalars: local Pippenger over its point range, ONE
+ncclAllGather of the 96-byte partial points on the context-owned communicator, local sum (csrc/comm.cu).  Timed on the device
+(CUDA events around the whole call, MAX over ranks), uniform and witness-like scalars.  One JSON line per size on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
         tools/msm_sharded_scaling.py "20,22,24,26"
@@ -20,7 +20,6 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, _ROOT)
 sys.path.insert(0, os.path.join(_ROOT, "tools"))
 zk = importlib.import_module("scroll-prover_b200")
-multi = importlib.import_module("scroll-prover_b200.multi")
 from quick_time import rand_fr  # noqa: E402
 
 
@@ -34,14 +33,16 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        ctx.comm_init_torch(dist)
     sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "20,22,24,26").split(",")]
     for log_n in sizes:
         n = 1 << log_n
-        lo, hi = multi.shard_range(n, rank, world)
-        m = hi - lo
-        g = torch.empty((m, 8), dtype=torch.int64, device="cuda")
-        ctx.g1_generator_mul_batch(rand_fr(m, 1000 * log_n + rank), out=g)
+        lo, m = zk.shard_range(n, rank, world)
+        g = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        ctx.g1_generator_mul_batch(rand_fr(n, 1000 * log_n), out=g)  # the same SRS on every rank
         srs = ctx.srs_register(g)
+        del g
         sc = rand_fr(m, 5000 * log_n + rank)
         sel = torch.rand(m, device="cuda")
         small = torch.zeros((m, 4), dtype=torch.int64, device="cuda")
@@ -59,7 +60,7 @@ def main():
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                multi.msm_sharded(lambda s: srs.msm(s), ctx.g1_sum, scal, dist if world > 1 else None, device=dev)
+                srs.msm_sharded(scal, n)
                 e1.record()
                 torch.cuda.synchronize()
                 t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -74,7 +75,7 @@ def main():
         if rank == 0:
             print(json.dumps(row), flush=True)
         srs.release()
-        del g, sc, wl, small
+        del sc, wl, small
         torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
