@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — chunk-proof polynomial-arithmetic wall time on B200 (BASELINE.json metric).
+"""bench.py — chunk-proof polynomial-arithmetic wall time on B200 (BASELINE.json metric, configs[2]).
 
-A "step" is ONE pass of the hot path over one proof's worth of synthetic columns: the KZG commits
-(MSM) and NTTs that halo2's create_proof issues for the degree-24 layer of a chunk proof
-(BASELINE.json configs[1], "inner-prove ... degree-24 SRS"; shape from
-/root/reference/integration/configs/layer1.config:3-9 as derived in SURVEY.md §8(d).2):
+A "step" is ONE pass of the hot path over one CHUNK PROOF's worth of synthetic columns: the KZG commits (MSM) and
+NTTs that halo2's create_proof issues for the three proofs `test-chunk-prove` generates on the degree-26 SRS
+(/root/reference/Makefile:41, integration/tests/chunk_tests.rs:17-24, integration/src/prove.rs:37-39):
 
-    28 columns  x [commit_lagrange = MSM 2^k  ->  lagrange_to_coeff = iNTT 2^k  ->  coeff_to_extended = coset NTT 2^(k+2)]
-     7 commits  of coefficient-form polynomials (4 quotient pieces + 3 SHPLONK)   = MSM 2^k over g
-     1 extended_to_coeff                                                            = inverse coset NTT 2^(k+2)
+    inner   zkEVM super-circuit,  k = 20 (INNER_DEGREE, integration/src/mock.rs:9): several hundred columns
+    layer1  wide compression,     k = 24 (integration/configs/layer1.config:3-9)
+    layer2  thin compression,     k = 25 (integration/configs/layer2.config:3-9; 11 MSMs by release-v0.13.1/chunk.protocol)
 
-19 of the 35 MSMs use witness-like scalars (60 % zero / 30 % < 2^16 / 10 % uniform), 16 uniform.  The
-real trace cannot be proved here (no Rust toolchain, no SRS files, host witness generation out of scope),
-so the polynomial-arithmetic layer is replayed on synthetic data of exactly that shape: "data": "synthetic".
+per layer:
+    C columns   x [commit_lagrange = MSM 2^k -> lagrange_to_coeff = iNTT 2^k -> coeff_to_extended = coset NTT 2^(k+2)]
+    M commits   of coefficient-form polynomials (4 quotient pieces + SHPLONK)       = MSM 2^k over g
+    X           coeff_to_extended of fixed / permutation polynomials (layer2 only)  = coset NTT 2^(k+2)
+    1           extended_to_coeff of the quotient                                  = inverse coset NTT 2^(k+2)
+The layers run one after the other (each verifies the previous proof).  Column counts of the inner proof are the
+survey's estimate ("several hundred"), stated in `config`.  The real trace cannot be proved here (no Rust toolchain, no
+SRS files, host witness generation out of scope), so the layer is replayed on synthetic data of that shape.
 
-JSON keys: see README/DESIGN.md "Measurement".  `value` = device-resident seconds per step (inputs in HBM),
-`e2e` = the same step through the public session API with HOST (pinned) columns, H2D inside the timed region,
-commitments read back.  With --gpus N (torchrun) the step's independent jobs are fanned out over the ranks
-(strong scaling, no data-path collective; one tiny NCCL all_gather of the commitments).
+`--k K` replays ONE layer of the layer-1 shape at degree K instead (size sweeps; K = 24 is BASELINE configs[1]).
 
---impl reference times the CPU restatement of the reference's Rayon path (oracle/, all host threads) on a
-bounded sample of the same step; the default arm never touches oracle/ outside its `cpu_baseline` leg.
+JSON keys: see DESIGN.md "Measurement".  `value` = device-resident seconds per step (inputs in HBM), `e2e` = the same
+step through the public session API with HOST (pinned) witness columns, H2D inside the timed region, commitments read
+back.  With --gpus N (torchrun) every layer's independent jobs are fanned out over the ranks (strong scaling; the only
+exchange is one all-gather of the 96 B commitments per layer).
+
+--impl reference times the CPU restatement of the reference's Rayon path (oracle/, all host threads): every timed
+iteration runs one operation of each kind of each layer AT FULL SIZE and the step is those times multiplied by the op
+counts (`extrapolated_by_op_counts`); nothing is rescaled from smaller sizes, warm-up iterations never feed the value.
+The default arm never touches oracle/ outside its `cpu_baseline` leg.
 """
 from __future__ import annotations
 
@@ -32,34 +40,65 @@ import subprocess
 import sys
 import threading
 import time
+from collections import namedtuple
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_WITNESS_COLS, N_UNIFORM_COLS, N_COEFF_MSMS = 19, 9, 7
-def metric_name(k: int) -> str:
-    return f"chunk-proof wall-sec (degree-{k} layer poly-arith replay)"
-# measured on this pool's B200 (profiles/microbench_r01.jsonl): sustained Montgomery products/s and the
-# INT32 multiply-pipe rate they imply; nominal = 148 SM x 32 IMAD.WIDE lanes/clk x 1.965 GHz
-IMAD_PEAK_MEASURED_GMAC32 = 8500.0
-IMAD_PEAK_NOMINAL_GMAC32 = 9307.0
 MAC32_PER_MADD = 1280  # 10 modmul x 128 MAC32
 
+# name, k, witness-like Lagrange columns, uniform Lagrange columns, coefficient-form commits, extra coset NTTs
+Layer = namedtuple("Layer", "name k wit uni coeff extra")
+# inner: estimate for the zkEVM super-circuit (SURVEY.md §8(a) a5 "several hundred"): ~400 advice / lookup-multiplicity
+# columns (witness-like), ~100 permutation-z / lookup-phi / random columns (uniform), 4 quotient pieces + 2 SHPLONK commits
+# layer1: 15 advice + 2 lookup advice (layer1.config) -> 19 witness-like + 9 z / phi / random, 4 + 3 coefficient commits
+# layer2: chunk.protocol num_witness [1,1,3] -> 5 Lagrange commits; 4 quotient pieces + 2 SHPLONK commits = 11 MSMs;
+#         12 coset NTTs in all: the 5 witness columns + the 7 fixed / permutation polynomials
+CHUNK_LAYERS = (Layer("inner", 20, 416, 96, 6, 0), Layer("layer1", 24, 19, 9, 7, 0), Layer("layer2", 25, 3, 2, 6, 7))
 
-def workload_desc(k: int) -> str:
-    return (f"configs[1] inner-prove degree-{k} layer shape replay: {N_WITNESS_COLS + N_UNIFORM_COLS} columns x "
-            f"(MSM 2^{k} + iNTT 2^{k} + cosetNTT 2^{k + 2}) + {N_COEFF_MSMS} MSM 2^{k} + 1 icosetNTT 2^{k + 2}")
+
+def layers_for(args):
+    if args.k:
+        return (Layer(f"degree-{args.k} layer", args.k, 19, 9, 7, 0),)
+    return tuple(l._replace(k=max(2, l.k - args.shrink)) for l in CHUNK_LAYERS)
 
 
-def make_jobs():
-    """(kind, scalar distribution, relative cost) for every independent unit of the step."""
+def metric_name(args) -> str:
+    if args.k:
+        return f"chunk-proof wall-sec (degree-{args.k} layer poly-arith replay)"
+    return "chunk-proof wall-sec (degree-26 SRS: k=20+24+25 replay)" + (f" [sizes shrunk by 2^{args.shrink}]" if args.shrink else "")
+
+
+def workload_desc(args) -> str:
+    ls = layers_for(args)
+    per = "; ".join(f"{l.name} k={l.k}: {l.wit + l.uni} x (MSM 2^{l.k} + iNTT 2^{l.k} + cosetNTT 2^{l.k + 2}) + {l.coeff} MSM 2^{l.k}"
+                    + (f" + {l.extra} cosetNTT 2^{l.k + 2}" if l.extra else "") + f" + 1 icosetNTT 2^{l.k + 2}" for l in ls)
+    head = "configs[1] inner-prove degree-%d layer shape replay" % args.k if args.k else \
+        "configs[2] test-chunk-prove (degree-26 SRS) replay, three proofs in sequence"
+    return f"{head}: {per}"
+
+
+# relative job costs in ms, measured on one B200 (profiles/sweep_r01.jsonl and this round's batch figures); only the
+# balance of the fan-out depends on them
+def _cost(kind: str, dist: str, k: int) -> float:
+    s = 2.0 ** (k - 24)
+    if kind in ("lmsm", "msm"):
+        return (9.6 if dist == "w" else 42.0) * s * (1.0 if k >= 22 else 0.9)
+    if kind == "ntt":
+        return 19.5 * s
+    return 16.0 * s  # coset / icoset
+
+
+def make_jobs(layer: Layer):
+    """(kind, scalar distribution, relative cost) for every independent unit of one layer's proof."""
     # A column's commitment (MSM) and its transforms (iNTT + coset NTT) are independent, so they are separate jobs.
-    # relative costs measured on B200 at k = 24 (ms): witness-like MSM 11, uniform MSM 44, transform chain 18, icoset 16
-    jobs = [("lmsm", "w", 11.0)] * N_WITNESS_COLS + [("lmsm", "u", 44.0)] * N_UNIFORM_COLS   # commit_lagrange
-    jobs += [("ntt", "w", 18.0)] * N_WITNESS_COLS + [("ntt", "u", 18.0)] * N_UNIFORM_COLS      # lagrange_to_coeff + coeff_to_extended
-    jobs += [("msm", "u", 44.0)] * N_COEFF_MSMS + [("icoset", "u", 16.0)]
+    k = layer.k
+    jobs = [("lmsm", "w", _cost("lmsm", "w", k))] * layer.wit + [("lmsm", "u", _cost("lmsm", "u", k))] * layer.uni   # commit_lagrange
+    jobs += [("ntt", "w", _cost("ntt", "w", k))] * layer.wit + [("ntt", "u", _cost("ntt", "u", k))] * layer.uni      # lagrange_to_coeff + coeff_to_extended
+    jobs += [("msm", "u", _cost("msm", "u", k))] * layer.coeff + [("coset", "u", _cost("coset", "u", k))] * layer.extra
+    jobs += [("icoset", "u", _cost("icoset", "u", k))]
     return jobs
 
 
@@ -73,6 +112,12 @@ def assign_jobs(jobs, world: int):
         out[r].append(jobs[i])
         load[r] += jobs[i][2]
     return out
+
+
+def op_counts(layer: Layer):
+    """operations of one layer by kind (the multipliers of the CPU arm's per-op times)"""
+    return {"msm_w": layer.wit, "msm_u": layer.uni + layer.coeff, "intt": layer.wit + layer.uni,
+            "coset": layer.wit + layer.uni + layer.extra + 1}  # the quotient's inverse coset NTT costs one coset NTT
 
 
 def host_threads() -> int:
@@ -121,6 +166,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def imad_peak():
+    """INT32 multiply-pipe peaks (GMAC32/s): `measured` from the tracked, clock-stamped microbenchmark record
+    IMAD_PEAK.json (written by tools/imad_peak.py on a B200), `nominal` = SMs x 32 IMAD.WIDE lanes/clk x max SM clock."""
+    d = json.load(open(os.path.join(ROOT, "IMAD_PEAK.json")))
+    return d["montgomery_product_gmac32"], d["nominal_imad_wide_gmac32"], d
+
+
 # ====================================================================================================
 # reference arm / cpu_baseline: the oracle's restatement of halo2_proofs' Rayon path on the host cores
 # ====================================================================================================
@@ -137,36 +189,50 @@ def _cpu_inputs(k: int, threads: int):
     return _CPU_INPUTS[k]
 
 
-def cpu_sample(k: int, threads: int, calibrate: bool = True):
-    """Times a bounded sample of the step on the CPU: 1 witness-like MSM, 1 uniform MSM, 1 iNTT 2^k,
-    1 coset NTT 2^(k+2); the step is extrapolated by op counts.  Returns (step_seconds, detail)."""
+def cpu_layer_sample(k: int, threads: int):
+    """One operation of each kind at FULL size on `threads` host threads: witness-like MSM 2^k, uniform MSM 2^k,
+    iNTT 2^k, coset NTT 2^(k+2).  Returns {op: seconds}."""
     from oracle import oracle as O  # ORACLE: allowed here only (cpu_baseline / --impl reference)
 
-    n = 1 << k
     bases, sw, su, dom = _cpu_inputs(k, threads)
     t = {}
     t0 = time.perf_counter(); O.best_multiexp(sw, bases, threads); t["msm_w"] = time.perf_counter() - t0
     t0 = time.perf_counter(); O.best_multiexp(su, bases, threads); t["msm_u"] = time.perf_counter() - t0
     t0 = time.perf_counter(); coeff = dom.lagrange_to_coeff(su, threads); t["intt"] = time.perf_counter() - t0
     t0 = time.perf_counter(); dom.coeff_to_extended(coeff, threads); t["coset"] = time.perf_counter() - t0
-    if calibrate:
-        # how many of the nominal host threads actually run in parallel (containers are often CPU-quota limited):
-        # one 2^14-point chunk alone vs one such chunk per thread, all at once
-        m = min(1 << 14, n)
-        reps = np.tile(su[:m], (threads, 1)); rb = np.tile(bases[:m], (threads, 1))
-        t1 = tT = 1e30
-        for _ in range(2):
-            t0 = time.perf_counter(); O.best_multiexp(su[:m], bases[:m], 1); t1 = min(t1, time.perf_counter() - t0)
-            t0 = time.perf_counter(); O.best_multiexp(reps, rb, threads); tT = min(tT, time.perf_counter() - t0)
-        t["effective_parallelism"] = round(threads * t1 / tT, 1) if tT > 0 else None
-        t["affinity"] = len(os.sched_getaffinity(0))
-        for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
-            if os.path.exists(f):
-                t["cgroup_cpu"] = open(f).read().strip()
-                break
-    step = (N_WITNESS_COLS * t["msm_w"] + (N_UNIFORM_COLS + N_COEFF_MSMS) * t["msm_u"]
-            + (N_WITNESS_COLS + N_UNIFORM_COLS) * (t["intt"] + t["coset"]) + t["coset"])
-    return step, t
+    return t
+
+
+def cpu_parallelism(threads: int):
+    """how many of the nominal host threads actually run in parallel (containers are often CPU-quota limited):
+    one 2^14-point MSM chunk alone vs one such chunk per thread, all at once"""
+    from oracle import oracle as O  # ORACLE: allowed here only (cpu_baseline / --impl reference)
+
+    m = 1 << 14
+    bases, su = O.fill_points_chain(m, 7, threads), O.fill_fr(m, 2, False)
+    reps, rb = np.tile(su, (threads, 1)), np.tile(bases, (threads, 1))
+    t1 = tT = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter(); O.best_multiexp(su, bases, 1); t1 = min(t1, time.perf_counter() - t0)
+        t0 = time.perf_counter(); O.best_multiexp(reps, rb, threads); tT = min(tT, time.perf_counter() - t0)
+    out = {"effective_parallelism": round(threads * t1 / tT, 1) if tT > 0 else None, "affinity": len(os.sched_getaffinity(0))}
+    for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        if os.path.exists(f):
+            out["cgroup_cpu"] = open(f).read().strip()
+            break
+    return out
+
+
+def cpu_step_sample(layers, threads: int):
+    """(step seconds, per-layer detail): every layer's four operations timed once at full size, times the op counts"""
+    total, detail = 0.0, {}
+    for l in layers:
+        t = cpu_layer_sample(l.k, threads)
+        cnt = op_counts(l)
+        sec = sum(cnt[o] * t[o] for o in cnt)
+        detail[l.name] = {"k": l.k, "op_s": {o: round(v, 6) for o, v in t.items()}, "op_counts": cnt, "layer_s": sec}
+        total += sec
+    return total, detail
 
 
 def run_reference(args):
@@ -174,36 +240,33 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    _cpu_inputs(args.k, threads)
-    vals, detail, budget_s, t_start, reduced = [], None, 240.0, time.perf_counter(), 0
-    scale = None
-    for i in range(args.warmup + args.steps):
-        elapsed = time.perf_counter() - t_start
-        left = args.warmup + args.steps - i
-        if scale is not None and vals_full and elapsed + left * vals_full[-1][1] > budget_s and args.k >= 16:
-            # keep the whole run within a few minutes: the remaining iterations time the same ops two sizes down and
-            # are scaled by the full/small ratio measured on this box
-            st, _ = cpu_sample(args.k - 2, threads, calibrate=False)
-            step, reduced = st * scale, reduced + 1
-        else:
-            t0 = time.perf_counter()
-            step, detail = cpu_sample(args.k, threads, calibrate=(i == 0))
-            if i == 0:
-                vals_full = []
-                small, _ = cpu_sample(args.k - 2, threads, calibrate=False) if args.k >= 16 else (None, None)
-                scale = (step / small) if small else None
-            vals_full.append((step, time.perf_counter() - t0))
-        if i >= args.warmup:
-            vals.append(step)
+    layers = layers_for(args)
+    for l in layers:  # inputs (and the thread pool / page faults) outside every timed region
+        _cpu_inputs(l.k, threads)
+    small = tuple(l._replace(k=min(l.k, 12)) for l in layers)
+    for _ in range(args.warmup):  # warm-up never feeds the value: code paths and the thread pool at a small size
+        cpu_step_sample(small, threads)
+    budget_s, t_start, vals, detail = 240.0, time.perf_counter(), [], None
+    for i in range(args.steps):
+        if vals and (time.perf_counter() - t_start) + sample_wall > budget_s:
+            break  # the run stays within a few minutes: fewer full-size samples, never smaller ones
+        t0 = time.perf_counter()
+        v, detail = cpu_step_sample(layers, threads)
+        sample_wall = time.perf_counter() - t0
+        vals.append(v)
     v = sum(vals) / len(vals)
-    sample = ("per step: 1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d timed on %d host threads; step "
-              "extrapolated by op counts (19/16 MSM, 28 iNTT, 29 coset NTT); %d of %d iterations ran the same ops at 2^%d "
-              "scaled by the measured full/small ratio to bound the run" % (args.k, args.k, args.k + 2, threads, reduced,
-                                                                              args.warmup + args.steps, args.k - 2))
-    line = {"impl": "reference", "metric": metric_name(args.k), "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+    par = cpu_parallelism(threads)
+    sample = ("every timed sample: 1 witness-like MSM + 1 uniform MSM + 1 iNTT 2^k + 1 coset NTT 2^(k+2) per layer at FULL size "
+              "(k = %s) on %d host threads; step = op times x op counts; value = mean of %d full-size samples (of %d requested steps); "
+              "warm-up at 2^12, never in the value" % ("/".join(str(l.k) for l in layers), threads, len(vals), args.steps))
+    line = {"impl": "reference", "metric": metric_name(args), "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64x4 (254-bit Montgomery integers on the CPU)", "data": "synthetic", "config": {"workload": workload_desc(args.k), "k": args.k},
-            "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample, "detail_s": detail},
+            "dtype": "u64x4 (254-bit Montgomery integers on the CPU)", "data": "synthetic",
+            "config": {"workload": workload_desc(args), "k": args.k or None, "layers": [l._asdict() for l in layers]},
+            "extrapolated_by_op_counts": True, "full_size_samples": len(vals), "sample_values_s": vals,
+            "timed_cpu_seconds_per_sample": sample_wall,
+            "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample, "detail": detail,
+                             "parallelism": par},
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -229,12 +292,13 @@ def run_b200(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    k, n, ek = args.k, 1 << args.k, args.k + 2
+    layers = layers_for(args)
     comp = torch.cuda.Stream()  # a non-default stream, so that our CUDA events bracket the library's launches
     torch.cuda.set_stream(comp)
     ctx = zk.Context(local)
     ctx.set_stream(comp.cuda_stream)
-    dom = zk.EvaluationDomain(ctx, 5, k)
+    if dist:
+        ctx.comm_init_torch(dist)  # the context owns the NCCL communicator (sharded entry points)
 
     # ---- synthetic inputs (device-generated)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -257,63 +321,136 @@ def run_b200(args):
         torch.cuda.synchronize()
         return torch.where(m, uni, mont).contiguous()
 
-    cols = {"w": [witness_like(n) for _ in range(2)], "u": [rand_limbs(n) for _ in range(2)]}
-    hext = rand_limbs(1 << ek)
-    srs_scalars = rand_limbs(n)
-    g = torch.empty((n, 8), dtype=torch.int64, device=dev)
-    gl = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    # ---- SRS: the degree-26 SRS downsized per layer (ParamsKZG::downsize): `g` of a smaller degree is a prefix of the
+    # largest one, so ONE handle of the largest k serves every layer's coefficient-form commits; g_lagrange is per degree.
+    kmax = max(l.k for l in layers)
+    g = torch.empty((1 << kmax, 8), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
-    ctx.g1_generator_mul_batch(srs_scalars, out=g)
-    ctx.g1_generator_mul_batch(rand_limbs(n), out=gl)
-    params = zk.ParamsKZG(ctx, k, g, gl)
-    del g, gl, srs_scalars
-    my_jobs = assign_jobs(make_jobs(), world)[rank]
-    n_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
-    commits = np.zeros((len(my_jobs) + 1, 12), np.uint64)
+    ctx.g1_generator_mul_batch(rand_limbs(1 << kmax), out=g)
+    srs_g = ctx.srs_register(g, zk.SRS_G)
+    srs_gl = {}
+    for l in layers:
+        if l.k not in srs_gl:
+            ctx.g1_generator_mul_batch(rand_limbs(1 << l.k), out=g[: 1 << l.k])
+            srs_gl[l.k] = ctx.srs_register(g[: 1 << l.k], zk.SRS_G_LAGRANGE)
+    srs_g_small = {}  # a small layer commits over its own short `g` handle (tables sized for it) rather than a 2^25 prefix
+    for l in layers:
+        if l.k + 4 < kmax and l.k not in srs_g_small:
+            ctx.g1_generator_mul_batch(rand_limbs(1 << l.k), out=g[: 1 << l.k])
+            srs_g_small[l.k] = ctx.srs_register(g[: 1 << l.k], zk.SRS_G)
+    del g
+    torch.cuda.empty_cache()
 
-    lmsm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "lmsm"]
-    ntt_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "ntt"]
-    msm_jobs = [(j, job) for j, job in enumerate(my_jobs) if job[0] == "msm"]
-    has_icoset = any(job[0] == "icoset" for job in my_jobs)
+    # ---- per layer: this rank's jobs, inputs, output pools
+    RING_IN = 64   # distinct input columns per (layer, distribution) when a layer has more columns than that
+    plans = []
+    pool_coeff_bytes = pool_ext_bytes = 0
+    for l in layers:
+        n, ek = 1 << l.k, l.k + 2
+        my = assign_jobs(make_jobs(l), world)[rank]
+        lm = [j for j in my if j[0] == "lmsm"]
+        nt = [j for j in my if j[0] == "ntt"]
+        ms = [j for j in my if j[0] == "msm"]
+        cs = [j for j in my if j[0] == "coset"]
+        ic = [j for j in my if j[0] == "icoset"]
+        need = {"w": max(sum(1 for j in lm if j[1] == "w"), sum(1 for j in nt if j[1] == "w")),
+                "u": max(sum(1 for j in lm if j[1] == "u"), sum(1 for j in nt if j[1] == "u"))}
+        cols = {d: [(witness_like if d == "w" else rand_limbs)(n) for _ in range(min(need[d], RING_IN))] for d in ("w", "u")}
+        coeff_in = [rand_limbs(n) for _ in range(min(2, len(ms) + len(cs)))]   # device-produced polynomials (h pieces, openings, fixed)
+        hext = rand_limbs(1 << ek) if ic else None                              # device-produced quotient evaluations
+        dom = zk.EvaluationDomain(ctx, 5, l.k)
+        n_coeff_out = len(nt)
+        pool_coeff_bytes = max(pool_coeff_bytes, n_coeff_out * n * 32)
+        plans.append({"layer": l, "n": n, "ek": ek, "lm": lm, "nt": nt, "ms": ms, "cs": cs, "ic": ic, "cols": cols, "coeff_in": coeff_in,
+                      "hext": hext, "dom": dom, "my": my})
+    # output pools shared by the layers (they run one after the other): every transform chain keeps its OWN coefficient
+    # vector (the openings need them), the extended cosets go to a ring (evaluate_h consumes them group by group)
+    free_b, _ = torch.cuda.mem_get_info()
+    RING_EXT_BYTES = int(min(16 << 30, max(1 << 20, 0.25 * free_b)))
+    pool_coeff = torch.empty(max(pool_coeff_bytes, 32) // 8, dtype=torch.int64, device=dev)
+    pool_ext = torch.empty(RING_EXT_BYTES // 8, dtype=torch.int64, device=dev)
 
-    def job_list(src, hsrc):
-        """Everything this rank owns as ONE b200zk_run_column_jobs list: a column whose commitment and transforms both
-        landed here is one mode-2 job (uploaded once in the e2e arm); the quotient's extended_to_coeff is a mode-4 job."""
-        both = min(len(lmsm_jobs), len(ntt_jobs))
-        jl = [(src[job[1]][j % 2], params._gl, 2, None, None) for j, job in lmsm_jobs[:both]]
-        jl += [(src[job[1]][j % 2], params._gl, 0, None, None) for j, job in lmsm_jobs[both:]]
-        jl += [(src[job[1]][j % 2], None, 3, None, None) for j, job in ntt_jobs[both:]]
-        jl += [(src[job[1]][j % 2], params._g, 0, None, None) for j, job in msm_jobs]
-        if has_icoset:
-            jl.append((hsrc, None, 4, None, None))
-        return jl
+    def job_lists(pl, src_cols):
+        """this rank's share of one layer as ONE b200zk_run_column_jobs list: a column whose commitment and transforms both
+        landed here is one mode-2 job (uploaded once in the e2e arm)"""
+        l, n, ek = pl["layer"], pl["n"], pl["ek"]
+        gl = srs_gl[l.k]
+        gsrs = srs_g_small.get(l.k, srs_g)
+        ext_elems = (1 << ek) * 4
+        ring = max(1, pool_ext.numel() // ext_elems)
+        state = {"c": 0, "e": 0}
 
-    def run_jobs(jl):
+        def coeff_out():
+            o = pool_coeff[state["c"] * n * 4:(state["c"] + 1) * n * 4]
+            state["c"] += 1
+            return o
+
+        def ext_out():
+            o = pool_ext[(state["e"] % ring) * ext_elems:((state["e"] % ring) + 1) * ext_elems]
+            state["e"] += 1
+            return o
+
+        jl = []
+        for d in ("w", "u"):
+            lm = [j for j in pl["lm"] if j[1] == d]
+            nt = [j for j in pl["nt"] if j[1] == d]
+            both = min(len(lm), len(nt))
+            cs_ = src_cols[d]
+            pick = lambda i: cs_[i % len(cs_)]
+            jl += [(pick(i), gl, 2, coeff_out(), ext_out()) for i in range(both)]
+            jl += [(pick(i), gl, 0, None, None) for i in range(both, len(lm))]
+            jl += [(pick(i), None, 3, coeff_out(), ext_out()) for i in range(both, len(nt))]
+        ci = pl["coeff_in"]
+        jl += [(ci[i % len(ci)], gsrs, 0, None, None) for i in range(len(pl["ms"]))]
+        jl += [(ci[i % len(ci)], None, 5, None, ext_out()) for i in range(len(pl["cs"]))]
+        if pl["ic"]:
+            jl.append((pl["hext"], None, 4, pool_ext[:ext_elems], None))
+        return jl, ring
+
+    for pl in plans:
+        pl["resident"], pl["ring"] = job_lists(pl, pl["cols"])
+    # ---- e2e: the witness columns (every Lagrange-form column) start in pinned HOST memory; polynomials the prover
+    # produces on the device (quotient pieces, opening quotients, the quotient's evaluations) and the proving key's
+    # fixed / permutation polynomials are device-resident in a session and stay so
+    h2d_bytes = 0
+    for pl in plans:
+        host = {d: [c.cpu().pin_memory() for c in pl["cols"][d]] for d in ("w", "u")}
+        pl["host_jobs"], _ = job_lists(pl, host)
+        pl["h2d_bytes"] = sum(pl["n"] * 32 for j in pl["host_jobs"] if j[2] in (0, 1, 2, 3) and not j[0].is_cuda)
+        h2d_bytes += pl["h2d_bytes"]
+    total_jobs = sum(len(pl["resident"]) for pl in plans)
+    d2h_bytes = total_jobs * 96
+    commits = np.zeros((max(len(pl["resident"]) for pl in plans) + 1, 12), np.uint64)
+    gather_cap = max(len(pl["resident"]) for pl in plans) + 8
+    if dist:
+        cap_t = torch.tensor([gather_cap], device=dev)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+        gather_cap = int(cap_t.item())
+
+    def run_layer(pl, key):
+        jl = pl[key]
         if jl:
-            commits[: len(jl)] = zk.run_column_jobs(ctx, jl, k, omega_inv=dom.omega_inv, extended_omega=dom.extended_omega,
-                                                    extended_omega_inv=dom.extended_omega_inv, extended_k=ek)
+            commits[: len(jl)] = zk.run_column_jobs(ctx, jl, pl["layer"].k, omega_inv=pl["dom"].omega_inv,
+                                                    extended_omega=pl["dom"].extended_omega,
+                                                    extended_omega_inv=pl["dom"].extended_omega_inv, extended_k=pl["ek"])
         torch.cuda.current_stream().synchronize()
+        if dist:  # the next proof hashes this proof's commitments: one tiny all-gather per layer, the only exchange
+            t = torch.zeros((world, gather_cap, 12), dtype=torch.int64, device=dev)
+            mine = torch.zeros((gather_cap, 12), dtype=torch.int64, device=dev)
+            mine[: len(jl)] = torch.from_numpy(commits[: len(jl)].view(np.int64)).to(dev)
+            dist.all_gather_into_tensor(t.view(-1), mine.view(-1))
 
-    resident_jobs = job_list(cols, hext)
+    layer_ms = {"resident": [[] for _ in plans], "host_jobs": [[] for _ in plans]}
 
-    def step_resident():
-        """inputs already resident in HBM; the library runs the commitments and the transforms on two streams"""
-        run_jobs(resident_jobs)
-
-    # ---- e2e: host (pinned) columns -> session API; H2D of job j+1 overlaps compute of job j
-    host = {"w": [c.cpu().pin_memory() for c in cols["w"]], "u": [c.cpu().pin_memory() for c in cols["u"]],
-            "h": hext.cpu().pin_memory() if any(j[0] == "icoset" for j in my_jobs) else None}
-    # a column whose commitment and transforms are on the same rank crosses PCIe once (one mode-2 call)
-    _nl, _nn = sum(1 for j in my_jobs if j[0] == "lmsm"), sum(1 for j in my_jobs if j[0] == "ntt")
-    h2d_bytes = (max(_nl, _nn) + sum(1 for j in my_jobs if j[0] == "msm")) * n * 32 + \
-        sum((1 << ek) * 32 for j in my_jobs if j[0] == "icoset")
-
-    host_jobs = job_list(host, host["h"])
-    d2h_bytes = len(host_jobs) * 96  # the commitments array of the one run_column_jobs call
-
-    def step_e2e():
-        """the same job list from pinned HOST buffers: H2D of job j+1 on the library's copy stream while job j computes"""
-        run_jobs(host_jobs)
+    def step(key, record=False):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plans) + 1)] if record else None
+        if record:
+            evs[0].record(comp)
+        for i, pl in enumerate(plans):
+            run_layer(pl, key)
+            if record:
+                evs[i + 1].record(comp)
+        return evs
 
     def barrier():
         torch.cuda.synchronize()
@@ -321,18 +458,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_commits():
-        if not dist:
-            return
-        t = torch.zeros((world, 80, 12), dtype=torch.int64, device=dev)
-        mine = torch.zeros((80, 12), dtype=torch.int64, device=dev)
-        mine[: len(commits)] = torch.from_numpy(commits.view(np.int64)).to(dev)
-        dist.all_gather_into_tensor(t.view(-1), mine.view(-1))
-
-    def timed(step_fn, steps, warmup, profile=False):
+    def timed(key, steps, warmup, profile=False):
         for _ in range(warmup):
-            step_fn()
-            gather_commits()
+            step(key)
         barrier()
         if profile:
             ctx.profile_enable(True)
@@ -342,17 +470,17 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(comp)
-        for _ in range(steps):
-            step_fn()
-            gather_commits()
+        all_evs = [step(key, record=True) for _ in range(steps)]
         e1.record(comp)
         barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        for evs in all_evs:
+            for i in range(len(plans)):
+                layer_ms[key][i].append(evs[i].elapsed_time(evs[i + 1]))
         prof = ctx.profile_read() if profile else None
         if profile:
             prof["_actual_adds"] = ctx.msm_total_adds()
-        if profile:
             ctx.profile_enable(False)
         launches = ctx.launch_count() - l0
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -363,45 +491,49 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    sec, wall, _, launches = timed(step_resident, args.steps, args.warmup, profile=False)
+    sec, wall, _, launches = timed("resident", args.steps, args.warmup, profile=False)
     clocks = sampler.stop() if sampler else None
+    per_layer_value = [sum(v) / len(v) / 1e3 for v in layer_ms["resident"]]
     # per-kernel durations (roofline, kernel_ms_per_step) come from a separate profiled pass of the SAME step with the
     # two-stream overlap switched off: while kernels of two streams share the SMs their individual durations say nothing
     ctx.set_overlap(False)
     prof_steps = 1
-    _, _, prof, _ = timed(step_resident, prof_steps, 0, profile=True)
+    layer_ms["resident"] = [[] for _ in plans]
+    _, _, prof, _ = timed("resident", prof_steps, 0, profile=True)
     ctx.set_overlap(True)
     if args.skip_e2e:
-        e2e_sec = None
+        e2e_sec, per_layer_e2e = None, None
     else:
-        e2e_sec, e2e_wall, _, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+        e2e_sec, e2e_wall, _, _ = timed("host_jobs", max(1, min(args.steps, 3)), 1)
+        per_layer_e2e = [sum(v) / len(v) / 1e3 for v in layer_ms["host_jobs"]]
 
     # ---- units processed (whole job) for the throughput figures
-    st = ctx.msm_last_stats()
-    c_bits, W = st["window_bits"], st["n_windows"]
-    total_msm = N_WITNESS_COLS + N_UNIFORM_COLS + N_COEFF_MSMS
-    nw_adds = total_msm * n * W  # N*W upper bound (SURVEY §8(d) "G1-adds/s = N*W / t")
     bf = lambda lg: (1 << lg) // 2 * lg
-    total_bf = (N_WITNESS_COLS + N_UNIFORM_COLS) * (bf(k) + bf(ek)) + bf(ek)
+    total_bf = sum((l.wit + l.uni) * (bf(l.k) + bf(l.k + 2)) + (l.extra + 1) * bf(l.k + 2) for l in layers)
+    total_points = sum((l.wit + l.uni + l.coeff) * (1 << l.k) for l in layers)
 
-    line = None
     if rank == 0:
-        my_msm = sum(1 for j in my_jobs if j[0] in ("lmsm", "msm"))
+        peak_meas, peak_nom, peak_rec = imad_peak()
         actual_adds = prof.pop("_actual_adds")
         msm_ms = sum(prof[c]["ms"] for c in prof if c.startswith("msm_"))
-        acc_ms, acc_cnt = prof["msm_accumulate"]["ms"], prof["msm_accumulate"]["count"]
-        ntt_ms, ntt_cnt = prof["ntt_pass"]["ms"], prof["ntt_pass"]["count"]
-        my_bf = sum(bf(k) + bf(ek) for j in my_jobs if j[0] == "ntt") + sum(bf(ek) for j in my_jobs if j[0] == "icoset")
-        my_ntt_bytes = 0
-        for j in my_jobs:  # algorithmic HBM bytes: 64 B/element/pass, P = ceil(log_n / 8) passes in this build
-            if j[0] == "ntt":
-                my_ntt_bytes += 64 * n * 3 + 64 * (1 << ek) * 4
-            elif j[0] == "icoset":
-                my_ntt_bytes += 64 * (1 << ek) * 4
+        acc_ms = prof["msm_accumulate"]["ms"]
+        ntt_ms = prof["ntt_pass"]["ms"]
+        my_bf = my_ntt_bytes = my_points = 0
+        for pl in plans:
+            l, n, ek = pl["layer"], pl["n"], pl["ek"]
+            passes = lambda lg: (lg + 7) // 8  # this build: digits of <= 8 bits
+            for j in pl["my"]:
+                if j[0] == "ntt":
+                    my_bf += bf(l.k) + bf(ek)
+                    my_ntt_bytes += 64 * n * passes(l.k) + 64 * (1 << ek) * passes(ek)  # algorithmic: 64 B/element/pass
+                elif j[0] in ("coset", "icoset"):
+                    my_bf += bf(ek)
+                    my_ntt_bytes += 64 * (1 << ek) * passes(ek)
+                else:
+                    my_points += n
         # algorithmic MAC32 of the accumulate launches = bucket additions actually performed (non-zero signed digits;
         # witness-like columns skip most of the N*W upper bound) x 1280 MAC32 per mixed add
         acc_achieved = (actual_adds * MAC32_PER_MADD) / (acc_ms * 1e-3) / 1e9 if acc_ms else None
-        steps_prof = prof_steps
         traffic, traffic_note = None, None
         try:  # DRAM bytes of one msm_accumulate launch from the committed `ncu --set full` capture (uniform 2^24 MSM)
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_v6_summary.json")))
@@ -416,41 +548,51 @@ def run_b200(args):
             pass
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ntt_gbs = my_ntt_bytes * steps_prof / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
+        ntt_gbs = my_ntt_bytes * prof_steps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            cs, detail = cpu_sample(k, threads)
-            cpu = {"value": cs, "unit": "s", "cores": threads, "kind": "port",
-                   "sample": "1 witness-like + 1 uniform MSM 2^%d, 1 iNTT 2^%d, 1 coset NTT 2^%d on all host threads; step "
-                             "extrapolated by op counts" % (k, k, ek), "detail_s": detail}
+            cs, detail = cpu_step_sample(layers, threads)
+            cpu = {"value": cs, "unit": "s", "cores": threads, "kind": "port", "extrapolated_by_op_counts": True,
+                   "sample": "ONE full-size sample: per layer 1 witness-like MSM + 1 uniform MSM + 1 iNTT 2^k + 1 coset NTT 2^(k+2) on "
+                             "all host threads; step = op times x op counts", "detail": detail}
+        st = ctx.msm_last_stats()
         line = {
-            "metric": metric_name(args.k), "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
-            "config": {"workload": workload_desc(k), "k": k, "msm_window_bits": c_bits, "msm_windows": W,
-                       "parallelism": f"job fan-out x{world} (no data-path collective)",
-                       "l2": "inputs (>= 512 MiB per column) exceed the 126 MB L2; no flush needed"},
-            "msm_g1_adds_per_s": (my_msm * n * W * steps_prof) / (msm_ms * 1e-3) if msm_ms else None,
-            "ntt_butterflies_per_s": (my_bf * steps_prof) / (ntt_ms * 1e-3) if ntt_ms else None,
-            "msm_actual_bucket_adds_per_step_rank0": actual_adds / steps_prof,
-            "job_g1_adds_per_s": nw_adds / sec, "job_ntt_butterflies_per_s": total_bf / sec,
+            "config": {"workload": workload_desc(args), "k": args.k or None, "layers": [l._asdict() for l in layers],
+                       "parallelism": f"per-layer job fan-out x{world} (no data-path collective; one 96 B/commitment all-gather per layer)",
+                       "buffers": {"distinct_input_columns_per_layer_and_distribution": RING_IN,
+                                   "coefficient_outputs": "one per transform chain (kept)",
+                                   "extended_outputs_ring": [pl["ring"] for pl in plans]},
+                       "l2": "inputs (>= 32 MiB per column, hundreds of distinct columns) exceed the 126 MB L2; no flush needed"},
+            "layers_s": {pl["layer"].name: v for pl, v in zip(plans, per_layer_value)},
+            "layers_e2e_s": {pl["layer"].name: v for pl, v in zip(plans, per_layer_e2e)} if per_layer_e2e else None,
+            "msm_points_per_s_in_kernels_rank0": my_points * prof_steps / (msm_ms * 1e-3) if msm_ms else None,
+            "ntt_butterflies_per_s": (my_bf * prof_steps) / (ntt_ms * 1e-3) if ntt_ms else None,
+            "msm_actual_bucket_adds_per_step_rank0": actual_adds / prof_steps,
+            "msm_g1_adds_per_s": actual_adds / (msm_ms * 1e-3) if msm_ms else None,
+            "job_msm_points_per_s": total_points / sec, "job_ntt_butterflies_per_s": total_bf / sec,
             "roofline": {"bound": "int32-imad", "kernel": "msm_accumulate", "achieved": acc_achieved,
-                         "peak": IMAD_PEAK_MEASURED_GMAC32, "peak_nominal": IMAD_PEAK_NOMINAL_GMAC32, "unit": "GMAC32/s",
-                         "frac": acc_achieved / IMAD_PEAK_MEASURED_GMAC32 if acc_achieved else None,
-                         "peak_source": "measured Montgomery-product microbenchmark (profiles/microbench_r01.jsonl), not in MEASURED_PEAKS.json",
+                         "peak": peak_meas, "peak_nominal": peak_nom, "unit": "GMAC32/s",
+                         "frac": acc_achieved / peak_meas if acc_achieved else None,
+                         "frac_of_nominal": acc_achieved / peak_nom if acc_achieved else None,
+                         "peak_source": "IMAD_PEAK.json (tracked; Montgomery-product microbenchmark with its clock record; "
+                                        "MEASURED_PEAKS.json has no INT32 figure): " + peak_rec.get("source", ""),
                          "traffic": traffic, "traffic_note": traffic_note,
                          "hbm": {"kernel": "ntt_pass", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": ntt_gbs / hbm_peak if ntt_gbs else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
-            "kernel_ms_per_step_rank0": {c: prof[c]["ms"] / steps_prof for c in prof if prof[c]["count"]},
+                                 "frac": ntt_gbs / hbm_peak if ntt_gbs else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}},
+            "kernel_ms_per_step_rank0": {c: prof[c]["ms"] / prof_steps for c in prof if prof[c]["count"]},
             "kernel_timing_note": "per-kernel CUDA-event durations and the roofline come from one extra profiled pass of the same "
                                   "step with the two-stream overlap off; `value` is measured with the overlap on and profiling off",
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "api": "ONE C-ABI call per step with pinned HOST buffers: b200zk_run_column_jobs (mode 2 for the 28 columns, "
-                           "mode 0 for the 7 coefficient commits, mode 4 for the quotient; H2D double-buffered on the library's "
-                           "copy stream; rank 0 bytes)"},
+                    "api": "ONE C-ABI call per proof (layer) with pinned HOST witness columns: b200zk_run_column_jobs (mode 2 per "
+                           "column, mode 0 coefficient commits, mode 5 / 4 for device-produced polynomials which stay resident); H2D "
+                           "double-buffered on the library's copy stream, commitments read back; rank 0 bytes"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_per_step": wall,
+            "msm_last_window": {"c": st["window_bits"], "W": st["n_windows"]},
         }
         print(json.dumps(line))
     if dist:
@@ -465,7 +607,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--k", type=int, default=24, help="log2 rows of the proved layer (24 = configs[1])")
+    ap.add_argument("--k", type=int, default=0, help="replay ONE layer of the layer-1 shape at this degree (sweeps; 24 = configs[1]); "
+                                                     "default 0 = the chunk proof of configs[2]: inner k=20 + layer1 k=24 + layer2 k=25")
+    ap.add_argument("--shrink", type=int, default=0, help="subtract from every layer's k (contract tests on small machines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident arm only")
     args = ap.parse_args()

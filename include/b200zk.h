@@ -103,6 +103,12 @@ B200ZK_API int32_t b200zk_srs_len(const b200zk_srs* srs, uint64_t* out);
  * result = sum_{i<n} scalars[i] * srs[i] as a normalised Jacobian point (x, y, 1), or (0, 1, 0) for the
  * identity.  n must be <= the SRS length (commit over the first n bases); n == 0 gives the identity. */
 B200ZK_API int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars, uint64_t n, void* out_jacobian96);
+/* `count` commitments over the SAME bases in one call: scalars[j] points to n scalars (host or device, independently),
+ * out_jacobian96 receives count x 96 B.  Columns go through the Pippenger pipeline in batches whose bucket sets lie side
+ * by side, so the latency-bound phases (scans, bucket reduction, final Horner) are paid once per batch -- the case of
+ * the several hundred 2^20-row columns of the inner (zkEVM super-circuit) proof.  Same results as count b200zk_msm_g1 calls. */
+B200ZK_API int32_t b200zk_msm_g1_batch(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* scalars, uint32_t count, uint64_t n,
+                                       void* out_jacobian96);
 /* same with explicit bases (generic best_multiexp; bases are uploaded for the call) */
 B200ZK_API int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96);
 /* partial MSM over the slice [first, first + n) of the registered bases: sum_{i<n} scalars[i] * srs[first + i]
@@ -150,14 +156,19 @@ B200ZK_API int32_t b200zk_ntt_fr_ext(b200zk_ctx* ctx, const void* in, uint32_t l
  *   mode 3: lagrange_to_coeff + coeff_to_extended only (no commitment; srs and commits_out may be NULL) -- lets a
  *           multi-GPU caller place a column's MSM and its transforms on different ranks
  * commits_out: count x 96 B normalised Jacobian points (host or device).  No host synchronisation inside the loop;
- * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs. */
+ * one D2H of the commitments at the end.  Replaces the per-column sequence in halo2_proofs/src/plonk/prover.rs.
+ * Jobs are processed in groups (up to 16 small columns): the upload of group g+1 overlaps the kernels of group g, and the
+ * commitments of consecutive jobs over the same SRS share one batched MSM pipeline (see b200zk_msm_g1_batch).
+ * A values pointer may also be DEVICE memory (a column that is already resident is used in place). */
 /* on (default): inside b200zk_run_column_jobs the commitments run on the context stream and the transforms on a second
  * stream, so the MSM's latency/memory-bound phases overlap with NTT butterflies; off: one stream (per-kernel timing). */
 B200ZK_API int32_t b200zk_ctx_set_overlap(b200zk_ctx* ctx, int on);
 /* Heterogeneous form: every job names its own host buffer, SRS and mode, so one proof phase (Lagrange commits,
  * coefficient-form commits, transforms, and the quotient's extended_to_coeff) is ONE call with a full copy/compute pipeline:
  *   mode 0..3 as above (host_values holds 2^k elements);
- *   mode 4: extended_to_coeff of 2^extended_k host values (inverse coset NTT) into coeff_out_dev or an internal scratch.
+ *   mode 4: extended_to_coeff of 2^extended_k host values (inverse coset NTT) into coeff_out_dev or an internal scratch;
+ *   mode 5: coeff_to_extended alone: 2^k COEFFICIENTS -> ext_out_dev (fixed / permutation polynomials whose cosets are
+ *           not kept, or a polynomial produced on the device).
  * commits_out gets count x 96 B; entries of jobs without a commitment are zero. */
 typedef struct b200zk_column_job {
     const void* host_values;

@@ -73,6 +73,7 @@ def _load():
         "b200zk_srs_len": [vp, C.POINTER(u64)],
         "b200zk_msm_g1": [vp, vp, vp, u64, vp],
         "b200zk_msm_g1_bases": [vp, vp, vp, u64, vp],
+        "b200zk_msm_g1_batch": [vp, vp, C.POINTER(vp), u32, u64, vp],
         "b200zk_msm_g1_range": [vp, vp, vp, u64, u64, vp],
         "b200zk_msm_g1_sharded": [vp, vp, vp, u64, vp],
         "b200zk_comm_unique_id": [vp],
@@ -127,7 +128,7 @@ def _load():
 ABI_SYMBOLS = [
     "b200zk_ctx_create", "b200zk_ctx_destroy", "b200zk_last_error", "b200zk_ctx_set_stream", "b200zk_ctx_synchronize",
     "b200zk_ctx_launch_count", "b200zk_buf_alloc", "b200zk_buf_free", "b200zk_buf_upload", "b200zk_buf_download",
-    "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_msm_g1_range", "b200zk_msm_g1_sharded",
+    "b200zk_srs_register", "b200zk_srs_set_precompute", "b200zk_srs_release", "b200zk_srs_len", "b200zk_msm_g1", "b200zk_msm_g1_bases", "b200zk_msm_g1_batch", "b200zk_msm_g1_range", "b200zk_msm_g1_sharded",
     "b200zk_comm_unique_id", "b200zk_ctx_comm_init", "b200zk_ctx_comm_info", "b200zk_shard_range", "b200zk_g1_sum",
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
@@ -518,6 +519,16 @@ class Srs:
         out = np.zeros(12, np.uint64)
         p, k = _ptr(scalars)
         self.ctx._ck(lib().b200zk_msm_g1(self.ctx._h, self._h, p, n, out.ctypes.data))
+        return out
+
+    def msm_batch(self, columns, n: int | None = None) -> np.ndarray:
+        """b200zk_msm_g1_batch: (count, 12) commitments of `columns` (host arrays / CUDA tensors) over the same bases."""
+        count = len(columns)
+        n = _count(columns[0], 32) if (n is None and count) else (n or 0)
+        keep = [_ptr(c) for c in columns]
+        arr = (C.c_void_p * max(count, 1))(*[p.value for p, _ in keep])
+        out = np.zeros((count, 12), np.uint64)
+        self.ctx._ck(lib().b200zk_msm_g1_batch(self.ctx._h, self._h, arr, count, n, out.ctypes.data))
         return out
 
     def msm_range(self, scalars, first: int, n: int | None = None) -> np.ndarray:

@@ -251,6 +251,48 @@ int32_t b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalar
     return msm_common(ctx, (const Affine*)srs->dev_bases, scalars, n, out_jacobian96, pre_c, srs->n);
 }
 
+int32_t b200zk_msm_g1_batch(b200zk_ctx* ctx, const b200zk_srs* srs, const void* const* scalars, uint32_t count, uint64_t n,
+                            void* out_jacobian96) {
+    CHECK_CTX(ctx);
+    if (!srs || (count && (!scalars || !out_jacobian96))) return fail(ctx, B200ZK_E_INVALID, "msm_g1_batch: null pointer");
+    if (srs->ctx != ctx) return fail(ctx, B200ZK_E_INVALID, "msm_g1_batch: SRS belongs to another context");
+    if (n > srs->n)
+        return fail(ctx, B200ZK_E_INVALID, "msm_g1_batch: %llu scalars but only %llu bases (assert_eq!(coeffs.len(), bases.len()))",
+                    (unsigned long long)n, (unsigned long long)srs->n);
+    for (uint32_t j = 0; j < count; ++j)
+        if (n && !scalars[j]) return fail(ctx, B200ZK_E_INVALID, "msm_g1_batch: scalars[%u] is null", j);
+    Guard g(ctx);
+    if (!count) return B200ZK_OK;
+    const uint32_t pre_c = (srs->pre_c && n * 16 >= srs->n) ? srs->pre_c : 0;
+    const uint32_t bmax = msm_max_batch(n, pre_c);
+    B2_TRY(scratch_reserve(ctx, ctx->stage_out, sizeof(Jacobian) * count));
+    Jacobian* res = (Jacobian*)ctx->stage_out.p;
+    size_t host_bytes = 0;  // staging for the host-resident columns of one batch
+    for (uint32_t j0 = 0; j0 < count; j0 += bmax) {
+        size_t b = 0;
+        for (uint32_t j = j0; j < count && j < j0 + bmax; ++j)
+            if (!is_device_ptr(scalars[j])) b += sizeof(Fr) * n;
+        if (b > host_bytes) host_bytes = b;
+    }
+    if (host_bytes) B2_TRY(scratch_reserve(ctx, ctx->stage_in, host_bytes));
+    std::vector<const Fr*> cols(bmax);
+    for (uint32_t j0 = 0; j0 < count; j0 += bmax) {
+        uint32_t len = count - j0 < bmax ? count - j0 : bmax;
+        size_t off = 0;
+        for (uint32_t q = 0; q < len; ++q) {
+            const void* p = scalars[j0 + q];
+            if (n && !is_device_ptr(p)) {
+                B2_TRY(h2d(ctx, (char*)ctx->stage_in.p + off, p, sizeof(Fr) * n));
+                p = (char*)ctx->stage_in.p + off;
+                off += sizeof(Fr) * n;
+            }
+            cols[q] = (const Fr*)p;
+        }
+        B2_TRY(msm_run_batch(ctx, (const Affine*)srs->dev_bases, cols.data(), len, n, res + j0, pre_c, srs->n));
+    }
+    return deliver(ctx, out_jacobian96, res, sizeof(Jacobian) * count);
+}
+
 int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96) {
     CHECK_CTX(ctx);
     if (!out_jacobian96 || (n && (!scalars || !g1_affine))) return fail(ctx, B200ZK_E_INVALID, "msm_g1_bases: null pointer");
