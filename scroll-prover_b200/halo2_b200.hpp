@@ -409,6 +409,11 @@ class GraphEvaluator {
         return ValueSource::Intermediate((uint32_t)calcs_.size() - 1);
     }
     size_t num_calculations() const { return calcs_.size(); }
+    // the program in the ABI's form (what b200zk_graph_create takes): for callers that run it through another backend
+    const std::vector<b200zk_calculation>& calculations() const { return calcs_; }
+    const std::vector<b200zk_value_source>& horner_parts() const { return parts_; }
+    const std::vector<Fr>& constants() const { return constants_; }
+    const std::vector<int32_t>& rotations() const { return rotations_; }
     // validation + lowering without a device (b200zk_graph_check): {instructions, on-chip slots}; throws Panic with the reason
     std::pair<uint32_t, uint32_t> check() const {
         uint32_t ni = 0, ns = 0;

@@ -186,6 +186,7 @@ inline Fq12 vertical(const G2Point& t, const G1Point& p) {
 // f *= line(T, Q)(P); T += Q   (handles T == Q, T == -Q, identities)
 inline void step(Fq12& f, G2Point& t, bool& t_inf, const G2Point& q, const G1Point& p) {
     if (t_inf) {  // the line is the constant 1 up to a factor killed by the final exponentiation
+        if (&q == &t) return;  // doubling the point at infinity: T stays at infinity (q aliases t in the doubling step)
         t = q;
         t_inf = false;
         return;
@@ -240,7 +241,8 @@ inline Fq12 final_exponentiation(const Fq12& f) {
 
 inline Fq12 pairing(const G1Point& p, const G2Point& q) { return final_exponentiation(miller_loop(p, q)); }
 
-// EIP-197 semantics: prod_i e(P_i, Q_i) == 1
+// prod_i e(P_i, Q_i) == 1 for TRUSTED, already validated points (no on-curve / subgroup checks here: see
+// pairing_check_validated below for the full EIP-197 input validation)
 inline bool pairing_check(const std::vector<std::pair<G1Point, G2Point>>& pairs) {
     Fq12 f = Fq12::one();
     for (const auto& pr : pairs) f = f * miller_loop(pr.first, pr.second);
@@ -301,6 +303,57 @@ inline bool g2_on_curve(const G2Point& q) {
     return q.y.sqr() == q.x.sqr() * q.x + b2;
 }
 
+// ---- G2 group law on the twist (affine; host-side tooling: [tau]G2 of a test SRS, the subgroup check) ----------------
+inline G2Point g2_add(const G2Point& a, const G2Point& b) {
+    if (a.is_identity()) return b;
+    if (b.is_identity()) return a;
+    Fq2 lambda;
+    if (a.x == b.x) {
+        if (!(a.y == b.y) || a.y.is_zero()) return {Fq2::zero(), Fq2::zero()};
+        Fq2 x2 = a.x.sqr();
+        lambda = (x2.dbl() + x2) * a.y.dbl().inv();
+    } else {
+        lambda = (b.y - a.y) * (b.x - a.x).inv();
+    }
+    Fq2 x3 = lambda.sqr() - a.x - b.x;
+    return {x3, lambda * (a.x - x3) - a.y};
+}
+// [s]Q, s given as 4 x u64 little-endian CANONICAL limbs (not Montgomery)
+inline G2Point g2_mul(const G2Point& q, const uint64_t s[4]) {
+    G2Point acc{Fq2::zero(), Fq2::zero()};
+    for (int i = 3; i >= 0; --i)
+        for (int b = 63; b >= 0; --b) {
+            acc = g2_add(acc, acc);
+            if ((s[i] >> b) & 1) acc = g2_add(acc, q);
+        }
+    return acc;
+}
+inline G2Point g2_generator() {  // halo2curves G2 generator = the constants of evm_verifier.yul:1230-1233
+    static const uint8_t be[128] = {
+        0x19, 0x8e, 0x93, 0x93, 0x92, 0x0d, 0x48, 0x3a, 0x72, 0x60, 0xbf, 0xb7, 0x31, 0xfb, 0x5d, 0x25, 0xf1, 0xaa, 0x49, 0x33, 0x35, 0xa9, 0xe7, 0x12, 0x97, 0xe4, 0x85, 0xb7, 0xae, 0xf3, 0x12, 0xc2,
+        0x18, 0x00, 0xde, 0xef, 0x12, 0x1f, 0x1e, 0x76, 0x42, 0x6a, 0x00, 0x66, 0x5e, 0x5c, 0x44, 0x79, 0x67, 0x43, 0x22, 0xd4, 0xf7, 0x5e, 0xda, 0xdd, 0x46, 0xde, 0xbd, 0x5c, 0xd9, 0x92, 0xf6, 0xed,
+        0x09, 0x06, 0x89, 0xd0, 0x58, 0x5f, 0xf0, 0x75, 0xec, 0x9e, 0x99, 0xad, 0x69, 0x0c, 0x33, 0x95, 0xbc, 0x4b, 0x31, 0x33, 0x70, 0xb3, 0x8e, 0xf3, 0x55, 0xac, 0xda, 0xdc, 0xd1, 0x22, 0x97, 0x5b,
+        0x12, 0xc8, 0x5e, 0xa5, 0xdb, 0x8c, 0x6d, 0xeb, 0x4a, 0xab, 0x71, 0x80, 0x8d, 0xcb, 0x40, 0x8f, 0xe3, 0xd1, 0xe7, 0x69, 0x0c, 0x43, 0xd3, 0x7b, 0x4c, 0xe6, 0xcc, 0x01, 0x66, 0xfa, 0x7d, 0xaa};
+    G2Point g;
+    g2_from_eip197(be, &g);
+    return g;
+}
+// Q in the r-torsion: [r]Q == O (G2's cofactor is not 1, so on-curve alone does not put a point in the pairing's domain)
+inline bool g2_in_subgroup(const G2Point& q) {
+    static const uint64_t r[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+    return g2_mul(q, r).is_identity();
+}
+// EIP-197 input validation in full: both points on their curves, the G2 point in the r-torsion
+inline bool pairing_check_validated(const std::vector<std::pair<G1Point, G2Point>>& pairs, bool* valid_input = nullptr) {
+    for (const auto& pr : pairs)
+        if (!g1_on_curve(pr.first) || !g2_on_curve(pr.second) || !g2_in_subgroup(pr.second)) {
+            if (valid_input) *valid_input = false;
+            return false;
+        }
+    if (valid_input) *valid_input = true;
+    return pairing_check(pairs);
+}
+
 // snark-verifier's KzgDecidingKey check for one accumulator: e(lhs, g2) * e(rhs, neg_s_g2) == 1
 inline bool verify_kzg_accumulator(const G1Point& lhs, const G1Point& rhs, const G2Point& g2, const G2Point& neg_s_g2) {
     if (!g1_on_curve(lhs) || !g1_on_curve(rhs) || !g2_on_curve(g2) || !g2_on_curve(neg_s_g2)) return false;
@@ -310,6 +363,7 @@ inline bool verify_kzg_accumulator(const G1Point& lhs, const G1Point& rhs, const
 //   e(C - y G, G2) * e(-W, [tau]G2 - x G2) == 1, rearranged to avoid G2 arithmetic:  e(C - y G + x W, G2) * e(-W, [tau]G2) == 1
 // (the caller supplies  lhs = C - y G + x W  and  W;  both are outputs of the device MSM / group ops)
 inline bool verify_kzg_opening(const G1Point& c_minus_yg_plus_xw, const G1Point& w, const G2Point& g2, const G2Point& tau_g2) {
+    if (!g1_on_curve(c_minus_yg_plus_xw) || !g1_on_curve(w) || !g2_on_curve(g2) || !g2_on_curve(tau_g2)) return false;
     G1Point nw = {w.x, w.y.neg()};
     return pairing_check({{c_minus_yg_plus_xw, g2}, {nw, tau_g2}});
 }

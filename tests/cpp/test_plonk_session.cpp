@@ -1,0 +1,221 @@
+// A create_proof / verify_proof session (scroll-prover_b200/plonk_b200.hpp) on a small multi-gate circuit with copy
+// constraints over two permutation column sets, one log-derivative lookup, an instance column and a rotated query:
+//   usage: test_plonk_session oracle|both [k] [seed]
+//   oracle: the prover runs over the CPU oracle (tests/cpp/oracle_ops.hpp) -- no CUDA device needed
+//   both:   additionally over the CUDA path through the C ABI (DeviceOps); the two proofs must be IDENTICAL BYTES
+// Prints `proof_sha_input <hex of the proof>` lines for the pytest wrapper (which hashes them and compares with the committed
+// digest), and checks: the proof verifies under the host pairing verifier; a flipped byte, a wrong instance, truncated /
+// extended proofs are rejected; a witness that breaks a gate / copy constraint / lookup cannot be proved into an accepted proof.
+#include <cstdio>
+#include <cstdlib>
+
+#include "oracle_ops.hpp"
+
+using namespace halo2_b200;
+using namespace halo2_b200::plonk;
+
+#define REQUIRE(c)                                                     \
+    do {                                                               \
+        if (!(c)) {                                                    \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                  \
+        }                                                              \
+    } while (0)
+
+struct Circuit {
+    ConstraintSystem cs;
+    std::vector<Poly> fixed;
+    std::unique_ptr<Assembly> assembly;
+    std::vector<Poly> advice, instances;
+};
+
+// fixed: 0 q_mul, 1 q_add, 2 q_lookup, 3 table, 4 q_pub, 5 q_rot, 6 constants        advice: 0 a, 1 b, 2 c        instance: 0
+static Circuit build(uint32_t k, uint64_t seed, int sabotage) {
+    Circuit C;
+    const uint64_t n = 1ull << k;
+    ConstraintSystem& cs = C.cs;
+    cs.num_fixed = 7;
+    cs.num_advice = 3;
+    cs.num_instance = 1;
+    auto a = Expr::advice(0), b = Expr::advice(1), c = Expr::advice(2);
+    cs.gates.push_back(Expr::mul(Expr::fixed(0), Expr::sub(Expr::mul(a, b), c)));                  // q_mul (a b - c)
+    cs.gates.push_back(Expr::mul(Expr::fixed(1), Expr::sub(Expr::sum(a, b), c)));                  // q_add (a + b - c)
+    cs.gates.push_back(Expr::mul(Expr::fixed(4), Expr::sub(a, Expr::instance(0))));                // q_pub (a - instance)
+    cs.gates.push_back(Expr::mul(Expr::fixed(5), Expr::sub(Expr::advice(0, 1), c)));               // q_rot (a(omega X) - c)
+    cs.gates.push_back(Expr::scaled(Expr::mul(Expr::fixed(0), Expr::fixed(1)), f_u64(3)));         // 3 q_mul q_add = 0 (selectors are exclusive)
+    Lookup lk;
+    lk.inputs = {Expr::mul(Expr::fixed(2), a)};                                                    // q_lookup * a  in  table
+    lk.table = {Expr::fixed(3)};
+    cs.lookups.push_back(lk);
+    cs.permutation = {{Expr::Advice, 0}, {Expr::Advice, 1}, {Expr::Advice, 2}, {Expr::Fixed, 6}};  // 4 columns -> two sets of <= 3
+    cs.finalize();
+    const uint32_t bf = cs.blinding_factors();
+    const uint64_t u = n - bf - 1;
+    C.fixed.assign(7, Poly(n, f_zero()));
+    C.advice.assign(3, Poly(n, f_zero()));
+    C.instances.assign(1, Poly(n, f_zero()));
+    C.assembly.reset(new Assembly(4, n));
+    Rng rng(seed * 77 + 5);
+    for (uint64_t r = 0; r < u; ++r) C.fixed[3][r] = f_u64(r);  // range table 0 .. u-1 (contains 0 for the disabled rows)
+    C.fixed[6][0] = f_u64(7);                                    // a constant, copied into b[3]
+    std::vector<int> a_forced(n, 0), b_forced(n, 0);
+    std::vector<Fr> a_val(n), b_val(n);
+    // planned copies (left is always produced before right is consumed)
+    struct Copy { int lc; uint64_t lr; int rc; uint64_t rr; };
+    std::vector<Copy> copies;
+    if (u > 12) {
+        copies.push_back({0, 1, 1, 5});    // a[1] = b[5]
+        copies.push_back({2, 2, 0, 7});    // c[2] = a[7]
+        copies.push_back({0, 1, 1, 10});   // a[1] = b[10]  (a cycle of three cells)
+        copies.push_back({3, 0, 1, 3});    // const[0] = b[3]
+        copies.push_back({2, 4, 1, 8});    // c[4] = b[8]
+    }
+    for (uint64_t r = 0; r < u; ++r) {
+        const bool is_mul = (r % 2 == 0), lookup_row = (r % 3 == 0), rot_row = (r % 5 == 1) && (r + 1 < u) && ((r + 1) % 3 != 0) && (r + 1 != 7);
+        C.fixed[is_mul ? 0 : 1][r] = f_one();
+        if (lookup_row) C.fixed[2][r] = f_one();
+        Fr av = a_forced[r] ? a_val[r] : (lookup_row ? f_u64(rng.next() % u) : rng.fr());
+        Fr bv = b_forced[r] ? b_val[r] : rng.fr();
+        Fr cv = is_mul ? f_mul(av, bv) : f_add(av, bv);
+        C.advice[0][r] = av;
+        C.advice[1][r] = bv;
+        C.advice[2][r] = cv;
+        if (rot_row) {
+            C.fixed[5][r] = f_one();
+            a_forced[r + 1] = 1;
+            a_val[r + 1] = cv;
+        }
+        for (auto& cp : copies) {
+            if (cp.lr != r) continue;
+            Fr v = cp.lc == 0 ? av : (cp.lc == 1 ? bv : (cp.lc == 2 ? cv : C.fixed[6][cp.lr]));
+            if (cp.rc == 0) { a_forced[cp.rr] = 1; a_val[cp.rr] = v; }
+            if (cp.rc == 1) { b_forced[cp.rr] = 1; b_val[cp.rr] = v; }
+        }
+    }
+    for (auto& cp : copies) C.assembly->copy((uint32_t)cp.lc, (uint32_t)cp.lr, (uint32_t)cp.rc, (uint32_t)cp.rr);
+    C.fixed[4][0] = f_one();              // row 0: a[0] is public
+    C.instances[0][0] = C.advice[0][0];
+    if (sabotage == 1) C.advice[2][4] = f_add(C.advice[2][4], f_one());        // breaks a gate (and a copy)
+    if (sabotage == 2) C.advice[1][5] = f_add(C.advice[1][5], f_one());        // breaks a copy constraint (and the add gate of row 5)
+    if (sabotage == 3) C.advice[0][3] = f_u64(u + 5);                          // lookup row 3: value outside the table
+    if (sabotage == 4) C.advice[2][6] = f_add(C.advice[2][6], f_one());        // breaks ONLY the mul gate of row 6: provable, but not acceptable
+    return C;
+}
+
+static std::string hex(const std::vector<uint8_t>& v) {
+    static const char* d = "0123456789abcdef";
+    std::string s;
+    for (uint8_t b : v) { s.push_back(d[b >> 4]); s.push_back(d[b & 15]); }
+    return s;
+}
+
+int main(int argc, char** argv) {
+    const std::string mode = argc > 1 ? argv[1] : "oracle";
+    if (mode == "blake2b") {  // blake2b <hex message>: the transcript's hash (personalisation "Halo2-Transcript"), for the hashlib cross-check
+        std::vector<uint8_t> msg;
+        const char* h = argc > 2 ? argv[2] : "";
+        for (size_t i = 0; h[i] && h[i + 1]; i += 2) {
+            unsigned v;
+            std::sscanf(h + i, "%2x", &v);
+            msg.push_back((uint8_t)v);
+        }
+        Blake2b st("Halo2-Transcript");
+        // fed in uneven pieces, with a finalize() in between (the transcript squeezes from a running state)
+        size_t cut = msg.size() / 3;
+        st.update(msg.data(), cut);
+        (void)st.finalize();
+        st.update(msg.data() + cut, msg.size() - cut);
+        auto d = st.finalize();
+        std::printf("%s\n", hex(std::vector<uint8_t>(d.begin(), d.end())).c_str());
+        return 0;
+    }
+    const uint32_t k = argc > 2 ? (uint32_t)std::atoi(argv[2]) : 6;
+    const uint64_t seed = argc > 3 ? (uint64_t)std::atoll(argv[3]) : 1;
+    const uint64_t n = 1ull << k;
+    try {
+        Circuit C = build(k, seed, 0);
+        REQUIRE(C.cs.degree() == 5 && C.cs.blinding_factors() == 5 && C.cs.permutation_chunk_len() == 3);
+        EvaluationDomain dom = EvaluationDomain::new_(C.cs.degree(), k);
+        REQUIRE(dom.extended_k == k + 2 && dom.quotient_poly_degree == 4);
+
+        // ParamsKZG::setup with a known tau (test SRS): g, g_lagrange from the oracle; [tau]G2 on the host
+        const Fr tau = f_from_bytes_wide((const uint8_t*)"b200zk test srs: tau is NOT secret -- a toxic-waste-free toy..!!");
+        std::vector<G1Affine> g(n), gl(n);
+        halo2_params_setup(k, reinterpret_cast<const fr_t*>(&tau), reinterpret_cast<g1_affine_t*>(g.data()), reinterpret_cast<g1_affine_t*>(gl.data()), 4);
+        VerifierParams vp;
+        vp.g2 = pairing::g2_generator();
+        {
+            uint8_t repr[32];
+            f_to_repr(tau, repr);
+            uint64_t limbs[4];
+            std::memcpy(limbs, repr, 32);
+            vp.s_g2 = pairing::g2_mul(vp.g2, limbs);
+        }
+        REQUIRE(pairing::g2_on_curve(vp.s_g2) && pairing::g2_in_subgroup(vp.s_g2) && pairing::g2_in_subgroup(vp.g2));
+
+        oracle_ops::OracleOps oops(g, gl, C.cs.degree(), k);
+        ProvingKey pk_o = keygen(oops, dom, C.cs, C.fixed, *C.assembly);
+        ProofArtifacts po = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB200 + seed);
+        std::printf("proof_bytes %zu commitments %zu evals %zu\n", po.proof.size(), po.n_commitments, po.n_evals);
+        REQUIRE(po.proof.size() == 32 * (po.n_commitments + po.n_evals));
+        std::printf("proof_sha_input oracle %s\n", hex(po.proof).c_str());
+        std::string why;
+        if (!verify_proof(dom, pk_o.vk, vp, C.instances, po.proof, &why)) std::printf("verify_proof rejected the honest proof: %s\n", why.c_str());
+        REQUIRE(verify_proof(dom, pk_o.vk, vp, C.instances, po.proof, &why));
+
+        // ---- the verifier is not vacuous
+        for (size_t pos : {size_t(5), po.proof.size() / 2, po.proof.size() - 40, po.proof.size() - 1}) {
+            std::vector<uint8_t> bad = po.proof;
+            bad[pos] ^= 0x01;
+            REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, bad, &why));
+        }
+        {
+            std::vector<Poly> wrong = C.instances;
+            wrong[0][0] = f_add(wrong[0][0], f_one());
+            REQUIRE(!verify_proof(dom, pk_o.vk, vp, wrong, po.proof, &why));
+            std::vector<uint8_t> shorter(po.proof.begin(), po.proof.end() - 32), longer = po.proof;
+            longer.push_back(0);
+            REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, shorter, &why) && !verify_proof(dom, pk_o.vk, vp, C.instances, longer, &why));
+            VerifierParams other = vp;
+            uint64_t two[4] = {2, 0, 0, 0};
+            other.s_g2 = pairing::g2_mul(vp.s_g2, two);  // another trusted setup
+            REQUIRE(!verify_proof(dom, pk_o.vk, other, C.instances, po.proof, &why));
+        }
+        // ---- unsatisfied witnesses: the prover either refuses (copy / lookup checks) or its proof is rejected (gates)
+        for (int sabotage = 1; sabotage <= 4; ++sabotage) {
+            Circuit B = build(k, seed, sabotage);
+            bool accepted = false;
+            try {
+                ProofArtifacts pb = create_proof(oops, dom, pk_o, B.advice, B.instances, 0xB200 + seed);
+                accepted = verify_proof(dom, pk_o.vk, vp, B.instances, pb.proof, &why);
+            } catch (const Panic&) {
+                accepted = false;
+            }
+            REQUIRE(!accepted);
+        }
+        // a different blinding seed gives a different, equally valid proof (zero-knowledge rows are really used)
+        ProofArtifacts po2 = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB201 + seed);
+        REQUIRE(po2.proof != po.proof && verify_proof(dom, pk_o.vk, vp, C.instances, po2.proof, &why));
+
+        if (mode == "both") {
+            ParamsKZG params;
+            ParamsKZG::setup(params, k, tau);  // on the device: g[i] = [tau^i]G, g_lagrange[i] = [L_i(tau)]G
+            REQUIRE(std::memcmp(params.g.data(), g.data(), 64 * n) == 0 && std::memcmp(params.g_lagrange.data(), gl.data(), 64 * n) == 0);
+            DeviceOps dops(params, dom);
+            ProvingKey pk_d = keygen(dops, dom, C.cs, C.fixed, *C.assembly);
+            REQUIRE(pk_d.vk.transcript_repr == pk_o.vk.transcript_repr);  // same fixed / permutation commitments
+            for (size_t i = 0; i < pk_o.fixed_cosets.size(); ++i) REQUIRE(pk_d.fixed_cosets[i] == pk_o.fixed_cosets[i]);
+            REQUIRE(pk_d.l_active_row == pk_o.l_active_row && pk_d.sigma_cosets == pk_o.sigma_cosets);
+            ProofArtifacts pd = create_proof(dops, dom, pk_d, C.advice, C.instances, 0xB200 + seed);
+            std::printf("proof_sha_input device %s\n", hex(pd.proof).c_str());
+            REQUIRE(pd.proof == po.proof);  // IDENTICAL PROOF BYTES: CUDA path == restated reference arithmetic
+            REQUIRE(verify_proof(dom, pk_d.vk, vp, C.instances, pd.proof, &why));
+            std::printf("device proof identical to the oracle's: %zu bytes\n", pd.proof.size());
+        }
+        std::printf("OK\n");
+        return 0;
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION: %s\n", e.what());
+        return 1;
+    }
+}

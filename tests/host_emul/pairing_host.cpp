@@ -12,7 +12,7 @@ extern "C" int pairing_host_eip197(const uint8_t* in, int n) {
         G1Point a;
         G2Point b;
         if (!fq_from_be32(p, &a.x) || !fq_from_be32(p + 32, &a.y) || !g2_from_eip197(p + 64, &b)) return -1;
-        if (!g1_on_curve(a) || !g2_on_curve(b)) return -1;
+        if (!g1_on_curve(a) || !g2_on_curve(b) || !g2_in_subgroup(b)) return -1;  // EIP-197 input validation
         pairs.push_back({a, b});
     }
     return pairing_check(pairs) ? 1 : 0;
