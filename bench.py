@@ -62,13 +62,15 @@ CHUNK_LAYERS = (Layer("inner", 20, 416, 96, 6, 0), Layer("layer1", 24, 19, 9, 7,
 def layers_for(args):
     if args.k:
         return (Layer(f"degree-{args.k} layer", args.k, 19, 9, 7, 0),)
-    return tuple(l._replace(k=max(2, l.k - args.shrink)) for l in CHUNK_LAYERS)
+    only = [x for x in getattr(args, "only", "").split(",") if x]
+    return tuple(l._replace(k=max(2, l.k - args.shrink)) for l in CHUNK_LAYERS if not only or l.name in only)
 
 
 def metric_name(args) -> str:
     if args.k:
         return f"chunk-proof wall-sec (degree-{args.k} layer poly-arith replay)"
-    return "chunk-proof wall-sec (degree-26 SRS: k=20+24+25 replay)" + (f" [sizes shrunk by 2^{args.shrink}]" if args.shrink else "")
+    return "chunk-proof wall-sec (degree-26 SRS: k=20+24+25 replay)" + (f" [sizes shrunk by 2^{args.shrink}]" if args.shrink else "") + \
+        (f" [only {args.only}]" if getattr(args, "only", "") else "")
 
 
 def workload_desc(args) -> str:
@@ -610,6 +612,7 @@ def main():
     ap.add_argument("--k", type=int, default=0, help="replay ONE layer of the layer-1 shape at this degree (sweeps; 24 = configs[1]); "
                                                      "default 0 = the chunk proof of configs[2]: inner k=20 + layer1 k=24 + layer2 k=25")
     ap.add_argument("--shrink", type=int, default=0, help="subtract from every layer's k (contract tests on small machines)")
+    ap.add_argument("--only", default="", help="profiling: restrict the chunk step to these layers, e.g. inner or layer1,layer2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident arm only")
     args = ap.parse_args()

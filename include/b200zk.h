@@ -15,7 +15,9 @@
  *    `Fr([u64;4])` / `Fq([u64;4])`; points are `G1Affine{x,y}` (64 B, identity = (0,0)) and
  *    `G1{x,y,z}` Jacobian (96 B, identity z = 0)            (pin: /root/reference/Cargo.lock:1911-1913).
  *  - every data pointer may be a host pointer OR a device pointer (detected with
- *    cudaPointerGetAttributes); host data is staged through pinned buffers inside the call.
+ *    cudaPointerGetAttributes); host inputs are copied to device staging buffers inside the call and are no
+ *    longer read once the call returns (pageable or pinned alike), host outputs are complete on return;
+ *    results delivered to DEVICE pointers are ordered on the context stream (b200zk_ctx_synchronize to wait).
  *  - one context per process per GPU (one process per GPU is the deployment model); a context is
  *    safe to call from several host threads (calls serialise on the context's stream).
  *  - there is NO CPU fallback: without a CUDA device b200zk_ctx_create fails with B200ZK_E_CUDA.

@@ -289,6 +289,8 @@ int32_t b200zk_msm_g1_batch(b200zk_ctx* ctx, const b200zk_srs* srs, const void* 
             cols[q] = (const Fr*)p;
         }
         B2_TRY(msm_run_batch(ctx, (const Affine*)srs->dev_bases, cols.data(), len, n, res + j0, pre_c, srs->n));
+        // the staging buffer is reused by the next batch, and the caller's host columns must not be read after we return
+        if (host_bytes && (j0 + bmax < count || is_device_ptr(out_jacobian96))) B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return deliver(ctx, out_jacobian96, res, sizeof(Jacobian) * count);
 }

@@ -206,7 +206,20 @@ inline int32_t d2h(b200zk_ctx* ctx, void* host, const void* dev, size_t bytes) {
     return B200ZK_OK;
 }
 
+inline bool is_pinned_host_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // Input staging: returns a device pointer holding `bytes` of `p` (p itself if already on device).
+// The caller's HOST buffer is no longer read once this returns: a copy from pageable memory has left the buffer when
+// cudaMemcpyAsync returns (the runtime stages it), a copy from PINNED memory is truly asynchronous, so it is waited for here --
+// an entry point whose result stays on the device would otherwise return while the DMA still reads the caller's memory.
 inline int32_t stage_in(b200zk_ctx* ctx, Scratch& s, const void* p, size_t bytes, const void** out) {
     if (is_device_ptr(p)) {
         *out = p;
@@ -214,6 +227,7 @@ inline int32_t stage_in(b200zk_ctx* ctx, Scratch& s, const void* p, size_t bytes
     }
     B2_TRY(scratch_reserve(ctx, s, bytes));
     B2_TRY(h2d(ctx, s.p, p, bytes));
+    if (bytes && is_pinned_host_ptr(p)) B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s.p;
     return B200ZK_OK;
 }

@@ -51,3 +51,31 @@ def test_sanitizer_logs_are_clean():
     race = open(os.path.join(ROOT, "profiles", "sanitizer_racecheck_r01.log")).read()
     assert "ERROR SUMMARY: 0 errors" in mem and "passed" in mem
     assert "0 hazards displayed (0 errors, 0 warnings)" in race and "passed" in race
+
+
+def test_round2_numbers_quoted_in_design_and_readme():
+    """the round-2 headline (BASELINE configs[2] step) and the multi-GPU / sharded / drop-in figures are the committed ones"""
+    DESIGN, README = _doc("DESIGN.md"), _doc("README.md")
+    v = bench("bench_r02_v1.json")
+    assert "configs[2]" in v["config"]["workload"] and [l["k"] for l in v["config"]["layers"]] == [20, 24, 25]
+    assert f"{v['value']:.3f} s" in DESIGN and f"{v['e2e']['value']:.3f} s" in DESIGN and f"{v['value']:.2f} s" in README
+    for name in ("inner", "layer1", "layer2"):
+        assert f"{v['layers_s'][name]:.3f}" in DESIGN, name
+    assert v["clocks"]["reasons"] == [] and v["clocks"]["sm_mhz"] == 1965 and v["gpu_launches"] > 0
+    assert 0.85 < v["roofline"]["frac"] < 1.0 and f"{v['roofline']['frac']:.2f}" in DESIGN and f"{v['roofline']['frac_of_nominal']:.2f}" in DESIGN
+    assert f"{v['cpu_baseline']['value']:.0f} s" in DESIGN and v["cpu_baseline"]["extrapolated_by_op_counts"] is True
+    v8 = bench("bench_r02_8gpu_v1.json")
+    assert v8["n_gpus"] == 8 and f"{v8['value']:.3f} s" in DESIGN and f"{v8['e2e']['value']:.3f} s" in DESIGN
+    for n_gpus in (1, 2, 4, 8):
+        rows = {r["log_n"]: r for r in jsonl(f"msm_sharded_r02_n{n_gpus}.jsonl")}
+        assert rows[26]["world"] == n_gpus
+        assert f"{rows[26]['uniform']['ms']:.2f} / {rows[26]['witness_like']['ms']:.2f}" in DESIGN, n_gpus
+    ab = {r["log_n"]: r for r in jsonl("affine_ab_r02.jsonl")}
+    assert ab[24]["uniform_equal"] and ab[24]["witness_equal"]
+    assert f"{ab[24]['affine_uniform_prof']['msm_accumulate']:.1f} ms" in DESIGN and f"{ab[24]['xyzz_uniform_prof']['msm_accumulate']:.1f} ms" in DESIGN
+    drop = {(r["op"], r["log_n"]): r for r in jsonl("dropin_r02.jsonl")}
+    assert f"{drop[('best_fft', 24)]['host_pinned_in_out_ms']:.1f} ms pinned" in DESIGN
+    g1 = {r["k"]: r for r in jsonl("g1fft_r02.jsonl")}
+    assert f"k = 21 {g1[21]['s_best']:.2f} s" in DESIGN
+    peak = json.load(open(os.path.join(ROOT, "IMAD_PEAK.json")))
+    assert peak["clocks"]["sm_mhz_median_under_load"] == 1965 and 8400 < peak["montgomery_product_gmac32"] < 8600
