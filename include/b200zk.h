@@ -295,6 +295,21 @@ B200ZK_API int32_t b200zk_graph_evaluate(b200zk_ctx* ctx, const b200zk_graph* gr
                                          const void* y32, const void* extended_omega32, void* values_dev, uint32_t log_size,
                                          int32_t rot_scale);
 
+/* The same for the rows [row_first, row_first + row_count) only: values[row] of the other rows is left untouched.  Column reads
+ * still wrap over the whole domain, so the columns must be complete on this device.  This is evaluate_h SHARDED BY ROW RANGE
+ * across GPUs: every rank holds the cosets, evaluates its b200zk_shard_range of the extended domain, and
+ * b200zk_allgather_rows makes the quotient numerator complete on every rank. */
+B200ZK_API int32_t b200zk_graph_evaluate_rows(b200zk_ctx* ctx, const b200zk_graph* graph, const void* const* fixed_dev,
+                                              uint32_t n_fixed, const void* const* advice_dev, uint32_t n_advice,
+                                              const void* const* instance_dev, uint32_t n_instance, const void* challenges32,
+                                              uint32_t n_challenges, const void* beta32, const void* gamma32, const void* theta32,
+                                              const void* y32, const void* extended_omega32, void* values_dev, uint32_t log_size,
+                                              int32_t rot_scale, uint64_t row_first, uint64_t row_count);
+/* Collective over the context's communicator: values_dev holds 2^log_size field elements of which this rank has written its
+ * b200zk_shard_range(2^log_size, rank, world) slice; afterwards every rank holds all slices (one in-place ncclAllGather of the
+ * 32-byte elements over NVLink, on the context stream).  world must divide 2^log_size (a power of two); world == 1 is a no-op. */
+B200ZK_API int32_t b200zk_allgather_rows(b200zk_ctx* ctx, void* values_dev, uint32_t log_size);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* element-wise Fr/Fq Montgomery product of two arrays on the device (field-layer parity tests) */
 B200ZK_API int32_t b200zk_debug_field_op(b200zk_ctx* ctx, int field /*0 Fr,1 Fq*/, int op /*0 mul,1 add,2 sub,3 inv*/,

@@ -108,6 +108,9 @@ def _load():
         "b200zk_graph_info": [vp, C.POINTER(u32), C.POINTER(u32)],
         "b200zk_graph_evaluate": [vp, vp, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp), u32, vp, u32, vp, vp, vp, vp, vp,
                                   vp, u32, i32],
+        "b200zk_graph_evaluate_rows": [vp, vp, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp), u32, vp, u32, vp, vp, vp, vp, vp,
+                                       vp, u32, i32, u64, u64],
+        "b200zk_allgather_rows": [vp, vp, u32],
         "b200zk_debug_field_op": [vp, C.c_int, C.c_int, vp, vp, vp, u64],
         "b200zk_profile_enable": [vp, C.c_int],
         "b200zk_profile_reset": [vp],
@@ -133,7 +136,7 @@ ABI_SYMBOLS = [
     "b200zk_g1_generator_mul_batch", "b200zk_fft_g1", "b200zk_g_to_lagrange", "b200zk_ntt_fr", "b200zk_ntt_fr_ext", "b200zk_ctx_set_overlap", "b200zk_run_column_jobs", "b200zk_commit_columns", "b200zk_poly_add", "b200zk_poly_sub",
     "b200zk_poly_mul", "b200zk_poly_scale", "b200zk_poly_axpy", "b200zk_eval_poly", "b200zk_inner_product", "b200zk_batch_invert",
     "b200zk_kate_division", "b200zk_prefix_scan", "b200zk_poly_lincomb", "b200zk_permutation_product", "b200zk_logup_running_sum", "b200zk_graph_create", "b200zk_graph_check",
-    "b200zk_graph_destroy", "b200zk_graph_info", "b200zk_graph_evaluate", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
+    "b200zk_graph_destroy", "b200zk_graph_info", "b200zk_graph_evaluate", "b200zk_graph_evaluate_rows", "b200zk_allgather_rows", "b200zk_debug_field_op", "b200zk_profile_enable", "b200zk_profile_reset", "b200zk_profile_read", "b200zk_msm_set_window", "b200zk_msm_last_stats", "b200zk_msm_total_adds",
 ]
 
 _lib = None
@@ -248,6 +251,13 @@ class Context:
             t = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(t, 0)
         self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def allgather_rows(self, values, log_size: int):
+        """b200zk_allgather_rows: collective; every rank contributes its shard_range slice of `values` (a CUDA tensor)."""
+        assert _count(values, 32) == 1 << log_size
+        pv, kv = _ptr(values)
+        self._ck(lib().b200zk_allgather_rows(self._h, pv, log_size))
+        return values
 
     def comm_info(self):
         r, w = C.c_int(), C.c_int()
@@ -624,9 +634,23 @@ class Graph:
         return {"n_instructions": ni.value, "n_slots": ns.value}
 
     def evaluate(self, values, log_size: int, rot_scale: int, fixed=(), advice=(), instance=(), challenges=None, beta=None,
-                 gamma=None, theta=None, y=None, extended_omega=None):
-        """values[row] = GraphEvaluator::evaluate(.., previous_value = values[row], ..) for every row of the extended domain."""
+                 gamma=None, theta=None, y=None, extended_omega=None, rows=None):
+        """values[row] = GraphEvaluator::evaluate(.., previous_value = values[row], ..) for every row of the extended domain
+        (rows = (first, count): only that slice -- evaluate_h sharded by row range, see Context.allgather_rows)."""
         assert _count(values, 32) == 1 << log_size
+        if rows is not None:
+            zero = np.zeros(4, np.uint64)
+            tf, kf = Context._dev_table(fixed)
+            ta, ka = Context._dev_table(advice)
+            ti, ki = Context._dev_table(instance)
+            ch = np.ascontiguousarray(np.asarray(challenges if challenges is not None else [], dtype=np.uint64).reshape(-1, 4))
+            sc = [_ptr(zero if v is None else v) for v in (beta, gamma, theta, y)]
+            pw, kw = _ptr(extended_omega)
+            pv, kv = _ptr(values)
+            self.ctx._ck(lib().b200zk_graph_evaluate_rows(self.ctx._h, self._h, tf, len(fixed), ta, len(advice), ti, len(instance),
+                                                          C.c_void_p(ch.ctypes.data) if len(ch) else None, len(ch), *[p for p, _ in sc], pw,
+                                                          pv, log_size, rot_scale, rows[0], rows[1]))
+            return values
         zero = np.zeros(4, np.uint64)
         tf, kf = Context._dev_table(fixed)
         ta, ka = Context._dev_table(advice)

@@ -136,6 +136,22 @@ int32_t b200zk_shard_range(uint64_t n, int rank, int world, uint64_t* first, uin
     return B200ZK_OK;
 }
 
+int32_t b200zk_allgather_rows(b200zk_ctx* ctx, void* values_dev, uint32_t log_size) {
+    if (!ctx) return B200ZK_E_INVALID;
+    if (!values_dev || log_size > 30) return fail(ctx, B200ZK_E_INVALID, "allgather_rows: bad arguments");
+    if (!is_device_ptr(values_dev)) return fail(ctx, B200ZK_E_INVALID, "allgather_rows: values must be device memory");
+    Guard g(ctx);
+    const uint64_t size = 1ull << log_size, world = (uint64_t)ctx->comm_world;
+    if (world == 1) return B200ZK_OK;
+    if (size % world) return fail(ctx, B200ZK_E_INVALID, "allgather_rows: world %llu does not divide 2^%u", (unsigned long long)world, log_size);
+    NcclApi* api = nccl_api();
+    const size_t bytes = sizeof(Fr) * (size / world);
+    char* base = (char*)values_dev;
+    // in place: the send buffer is this rank's slice inside the receive buffer
+    B2_NCCL(ctx, api, api->AllGather(base + bytes * (size_t)ctx->comm_rank, base, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return B200ZK_OK;
+}
+
 // partial MSM over the SRS slice [first, first + n)
 static int32_t msm_range_dev(b200zk_ctx* ctx, const b200zk_srs* srs, const void* scalars, uint64_t first, uint64_t n, Jacobian* res) {
     const void* sc_dev = nullptr;

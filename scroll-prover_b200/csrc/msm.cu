@@ -59,17 +59,16 @@ __device__ __forceinline__ void ld_affine(const Affine* p, Fq& x, Fq& y) {
 
 // every scalar once: canonical form, signed digits -> digits[w*n + i] (magnitude | sign<<31, 0 = skip) + histogram
 __global__ void __launch_bounds__(256) msm_count(MsmCols cols, uint64_t n, MsmPlan pl, uint32_t* hist, uint32_t* digits_all) {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total = n * pl.batch;
-    for (uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
-        const uint32_t col = (uint32_t)(gi / n);
-        const uint64_t i = gi - (uint64_t)col * n;
-        const Fr* scalars = cols.p[0];
+    // grid = (blocks over the scalars, column of the batch): no 64-bit division per element
+    const uint32_t col = blockIdx.y;
+    const Fr* scalars = cols.p[0];
 #pragma unroll
-        for (int q = 1; q < MSM_MAX_BATCH; ++q)
-            if (q == (int)col) scalars = cols.p[q];  // no dynamic indexing of kernel parameters
-        uint32_t* digits = digits_all + (uint64_t)col * pl.W * n;
-        uint32_t* hist_c = hist + (uint64_t)col * pl.Ws * pl.B;
+    for (int q = 1; q < MSM_MAX_BATCH; ++q)
+        if (q == (int)col) scalars = cols.p[q];  // no dynamic indexing of kernel parameters
+    uint32_t* digits = digits_all + (uint64_t)col * pl.W * n;
+    uint32_t* hist_c = hist + (uint64_t)col * pl.Ws * pl.B;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         Fr s = scalars[i];
         if (s.is_zero()) {
             for (uint32_t w = 0; w < pl.W; ++w) digits[(uint64_t)w * n + i] = 0;
@@ -114,23 +113,28 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
     uint32_t eff = 1;
     if (max_sweeps > 1) {
         uint64_t bytes = 4ull * (*total_entries);
-        eff = (uint32_t)((bytes + (200ull << 20) - 1) / (200ull << 20));
+        eff = (uint32_t)((bytes + (1ull << 28) - 1) >> 28);  // regions of <= 256 MiB (a shift: this runs once per thread)
         eff = eff < 1 ? 1 : (eff > max_sweeps ? max_sweeps : eff);
     }
     if (sweep >= eff) return;
-    const uint32_t b_lo = (uint32_t)((uint64_t)pl.B * sweep / eff), b_hi = (uint32_t)((uint64_t)pl.B * (sweep + 1) / eff);
-    uint64_t total = n * pl.W * pl.batch;
+    // B is a power of two and eff <= 4: the range bounds need no 64-bit division either
+    const uint32_t b_lo = eff == 3 ? (pl.B / 3) * sweep : (pl.B / eff) * sweep;
+    const uint32_t b_hi = (sweep + 1 == eff) ? pl.B : (eff == 3 ? (pl.B / 3) * (sweep + 1) : (pl.B / eff) * (sweep + 1));
+    // grid = (blocks over the scalars, col * W + w): the digits of one (column, window) are a contiguous run, so neither the
+    // window nor the column needs a 64-bit division per digit; blocks are still issued window-major (x fastest)
+    const uint32_t cw = blockIdx.y;
+    const uint32_t col = cw / pl.W, w = cw - col * pl.W;
+    const uint32_t* dg = digits + (uint64_t)cw * n;
+    uint32_t* cur = cursor + ((uint64_t)col * pl.Ws + (pl.Ws == 1 ? 0u : w)) * pl.B;
+    const uint32_t woff = (uint32_t)((uint64_t)w * pl.stride);
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        uint32_t d = digits[idx];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t d = dg[i];
         if (!d) continue;
         uint32_t bk = (d & 0x7fffffffu) - 1;
         if (bk < b_lo || bk >= b_hi) continue;
-        uint64_t cw = idx / n;  // col * W + w
-        uint32_t i = (uint32_t)(idx - cw * n);
-        uint64_t col = cw / pl.W, w = cw - col * pl.W;
-        uint32_t pos = atomicAdd(&cursor[(col * pl.Ws + (pl.Ws == 1 ? 0ull : w)) * pl.B + bk], 1u);
-        entries[pos] = (uint32_t)(i + w * pl.stride) | (d & 0x80000000u);
+        uint32_t pos = atomicAdd(&cur[bk], 1u);
+        entries[pos] = ((uint32_t)i + woff) | (d & 0x80000000u);
     }
 }
 
@@ -390,23 +394,39 @@ __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restr
 //   S = WS(Col) + 2^kc * WS(Row) + sum(Row),     WS(V) = sum_j j V_j = sum_{j>=1} Suffix_j(V)   (parallel suffix scan).
 static constexpr int RED_T = 128;   // 4 blocks/SM at 128 registers: the sums are latency-bound, more blocks in flight win
 
-__device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {  // result valid in thread 0
-    st_xyzz(sh + threadIdx.x, v);
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            XYZZ a = ld_xyzz(sh + threadIdx.x), b = ld_xyzz(sh + threadIdx.x + s);
-            xyzz_add(a, b);
-            st_xyzz(sh + threadIdx.x, a);
-        }
-        __syncthreads();
+// XYZZ sum over the lanes of a warp with register shuffles (32 x SHFL.DOWN per level, no shared-memory round trip, no block
+// barrier): after the call lane 0 holds the sum of the first `width` lanes (width a power of two <= 32).
+__device__ __forceinline__ void warp_xyzz_sum(XYZZ& v, int width = 32) {
+    Fq* f = &v.x;
+    for (int off = width >> 1; off > 0; off >>= 1) {
+        XYZZ o;
+        Fq* g = &o.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k].l.v[j] = __shfl_down_sync(0xffffffffu, f[k].l.v[j], off);
+        xyzz_add(v, o);
     }
-    v = ld_xyzz(sh);
+}
+
+// block sum: warp-shuffle reductions, one shared-memory hand-over between the warps.  Result valid in thread 0.
+// blockDim.x must be a multiple of 32 with a power-of-two number of warps (RED_T = 128: 4 warps).
+__device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {
+    warp_xyzz_sum(v);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (lane == 0) st_xyzz(sh + warp, v);
+    __syncthreads();
+    if (warp == 0) {
+        XYZZ t = lane < nwarps ? ld_xyzz(sh + lane) : XYZZ::identity();
+        warp_xyzz_sum(t, (int)nwarps);
+        v = t;
+    }
+    __syncthreads();  // sh may be reused by the caller
 }
 
 // grid = (rows + cols, Ws); block j < rows sums row j, block rows + j sums column j.  vec[set][0..rows) | [rows..rows+cols)
 __global__ void __launch_bounds__(RED_T, 4) msm_rowcol_sums(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t kc, XYZZ* __restrict__ vec) {
-    __shared__ XYZZ sh[RED_T];
+    __shared__ XYZZ sh[RED_T / 32];  // one slot per warp (block_tree_sum)
     const uint32_t cols = 1u << kc, rows = B >> kc;
     const XYZZ* bk = buckets + (uint64_t)blockIdx.y * B;
     XYZZ acc = XYZZ::identity();
@@ -434,7 +454,7 @@ __global__ void __launch_bounds__(RED_T, 4) msm_rowcol_sums(const XYZZ* __restri
 // blockIdx.x == q_max of the Row vector computes its plain total sum(Row).  out[set][which][b], stride (q_max + 1).
 __global__ void __launch_bounds__(RED_T, 4) msm_bit_sums(const XYZZ* __restrict__ vec, uint32_t B, uint32_t kc, uint32_t q_max,
                                                          XYZZ* __restrict__ out) {
-    __shared__ XYZZ sh[RED_T];
+    __shared__ XYZZ sh[RED_T / 32];  // one slot per warp (block_tree_sum)
     const uint32_t cols = 1u << kc, rows = B >> kc;
     const uint32_t which = blockIdx.y, b = blockIdx.x;
     const uint32_t m = which == 0 ? rows : cols;
@@ -648,11 +668,12 @@ int32_t msm_run_batch(b200zk_ctx* ctx, const Affine* bases, const Fr* const* col
     B2_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * pl.NB, st));
     uint32_t sblocks = (uint32_t)ctx->sm_count * 8;
     if (n) {
-        uint64_t want = (n * batch + 255) / 256;
-        uint32_t blocks = (uint32_t)(want < sblocks ? want : sblocks);
+        uint64_t want = (n + 255) / 256;
+        uint32_t per_col = (sblocks + batch - 1) / batch;
+        uint32_t blocks = (uint32_t)(want < per_col ? want : per_col);
         {
             ProfScope ps_(ctx, PROF_MSM_COUNT);
-            msm_count<<<blocks, 256, 0, st>>>(colp, n, pl, hist, digits);
+            msm_count<<<dim3(blocks, batch), 256, 0, st>>>(colp, n, pl, hist, digits);
         }
         B2_LAUNCH_CHECK(ctx);
     }
@@ -668,7 +689,7 @@ int32_t msm_run_batch(b200zk_ctx* ctx, const Affine* bases, const Fr* const* col
     if (n) {
         {
             ProfScope ps_(ctx, PROF_MSM_SCATTER);
-            uint64_t want = (max_entries + 1023) / 1024;  // 4 digits per thread, blocks issued in window-major order
+            uint64_t want = (n + 1023) / 1024;  // 4 digits per thread; grid.y = col * W + w, issued window-major (x fastest)
             uint32_t blocks = (uint32_t)(want < 0x7fffffffull ? (want ? want : 1) : 0x7fffffffull);
             {
                 uint32_t sweeps = 1;
@@ -682,7 +703,7 @@ int32_t msm_run_batch(b200zk_ctx* ctx, const Affine* bases, const Fr* const* col
                     if (ctx->msm_scatter_sweeps) sweeps = ctx->msm_scatter_sweeps;
                 }
                 for (uint32_t sw = 0; sw < sweeps; ++sw) {
-                    msm_scatter<<<blocks, 256, 0, st>>>(digits, n, pl, cursor, entries, offsets + pl.NB, sw, sweeps);
+                    msm_scatter<<<dim3(blocks, batch * pl.W), 256, 0, st>>>(digits, n, pl, cursor, entries, offsets + pl.NB, sw, sweeps);
                     if (sw + 1 < sweeps) B2_LAUNCH_CHECK(ctx);
                 }
             }

@@ -56,6 +56,7 @@ struct GraphLaunch {
     uint32_t uses_x, uses_prev;
     const Fr* xtab;  // omega_ext^j, j < size/2   (the level-log_size run of the twiddle table)
     Fr zeta;
+    uint64_t row_first, row_count;  // the rows this launch evaluates (a rank's slice of the extended domain)
 };
 
 // slot s of the row owned by thread `tid`: limb l at word (s * 8 + l) * T + tid  -- a warp reads 32 consecutive words
@@ -93,8 +94,9 @@ __global__ void graph_eval_kernel(GraphLaunch L) {
     extern __shared__ uint32_t gsm[];
     const uint32_t T = blockDim.x;
     const uint64_t size = 1ull << L.log_size;
-    const uint64_t row = (uint64_t)blockIdx.x * T + threadIdx.x;
-    if (row >= size) return;  // slots are private to a thread: no block-wide barrier below
+    const uint64_t idx = (uint64_t)blockIdx.x * T + threadIdx.x;
+    if (idx >= L.row_count) return;  // slots are private to a thread: no block-wide barrier below
+    const uint64_t row = L.row_first + idx;
     SmemSlots S{gsm + threadIdx.x, T};
     if (L.uses_prev) S.store(G_SLOT_PREV, q_ld(L.values + row));
     if (L.uses_x) {
@@ -142,8 +144,8 @@ int32_t graph_evaluate_run(b200zk_ctx* ctx, const b200zk_graph* g, GraphLaunch L
         B2_CUDA(ctx, cudaFuncSetAttribute(graph_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
         ctx->smem_optin |= 1u << 8;
     }
-    uint64_t size = 1ull << L.log_size;
-    uint32_t blocks = (uint32_t)((size + T - 1) / T);
+    uint32_t blocks = (uint32_t)((L.row_count + T - 1) / T);
+    if (!blocks) return B200ZK_OK;
     ProfScope ps_(ctx, PROF_POLY);
     graph_eval_kernel<<<blocks, T, smem, ctx->stream>>>(L);
     B2_LAUNCH_CHECK(ctx);
@@ -588,9 +590,22 @@ int32_t b200zk_graph_evaluate(b200zk_ctx* ctx, const b200zk_graph* graph, const 
                               const void* challenges32, uint32_t n_challenges, const void* beta32, const void* gamma32,
                               const void* theta32, const void* y32, const void* extended_omega32, void* values_dev, uint32_t log_size,
                               int32_t rot_scale) {
+    return b200zk_graph_evaluate_rows(ctx, graph, fixed_dev, n_fixed, advice_dev, n_advice, instance_dev, n_instance, challenges32,
+                                      n_challenges, beta32, gamma32, theta32, y32, extended_omega32, values_dev, log_size, rot_scale, 0,
+                                      log_size <= 30 ? (1ull << log_size) : 0);
+}
+
+int32_t b200zk_graph_evaluate_rows(b200zk_ctx* ctx, const b200zk_graph* graph, const void* const* fixed_dev, uint32_t n_fixed,
+                                   const void* const* advice_dev, uint32_t n_advice, const void* const* instance_dev, uint32_t n_instance,
+                                   const void* challenges32, uint32_t n_challenges, const void* beta32, const void* gamma32,
+                                   const void* theta32, const void* y32, const void* extended_omega32, void* values_dev, uint32_t log_size,
+                                   int32_t rot_scale, uint64_t row_first, uint64_t row_count) {
     CHECK_CTX(ctx);
     if (!graph) return fail(ctx, B200ZK_E_INVALID, "graph_evaluate: null graph");
     if (log_size > 30) return fail(ctx, B200ZK_E_INVALID, "graph_evaluate: log_size = %u > 30", log_size);
+    if (row_first > (1ull << log_size) || row_count > (1ull << log_size) - row_first)
+        return fail(ctx, B200ZK_E_INVALID, "graph_evaluate: rows [%llu, +%llu) exceed the domain of 2^%u", (unsigned long long)row_first,
+                    (unsigned long long)row_count, log_size);
     const GraphProgram& P = graph->prog;
     if (P.need_cols[0] > n_fixed || P.need_cols[1] > n_advice || P.need_cols[2] > n_instance)
         return fail(ctx, B200ZK_E_INVALID, "graph_evaluate: the program reads fixed/advice/instance columns up to %u/%u/%u, got %u/%u/%u",
@@ -635,6 +650,8 @@ int32_t b200zk_graph_evaluate(b200zk_ctx* ctx, const b200zk_graph* graph, const 
     L.uses_prev = P.uses_prev;
     L.xtab = nullptr;
     L.zeta = host_zeta();
+    L.row_first = row_first;
+    L.row_count = row_count;
     if (P.uses_x && log_size) {
         Fr w;
         B2_TRY(read_fr(ctx, extended_omega32, &w));

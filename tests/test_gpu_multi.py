@@ -50,6 +50,37 @@ def _worker(rank, world, port, q):
         allg = torch.empty((world, 12), dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(allg.view(-1), t)
         ok &= bool((allg == allg[0]).all().item())
+    # evaluate_h sharded by ROW RANGE: every rank evaluates its slice of the extended domain with a program that reads rotated
+    # columns (wrapping over the whole domain) and folds into the previous value, then one in-place all-gather over NVLink
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from quotient_programs import C_ADD, C_MUL, S_ADVICE, S_FIXED, S_INTER, S_PREV, S_Y  # noqa: E402
+
+    log_size = 12
+    size = 1 << log_size
+    cols = [O.fill_fr(size, 600 + i) for i in range(3)]
+    prev = O.fill_fr(size, 610)
+    yv = O.fr_from_int(12345)
+    prog = [(C_MUL, (S_ADVICE, 0, 1), (S_ADVICE, 1, 2), None), (C_ADD, (S_INTER, 0, 0), (S_FIXED, 0, 0), None),
+            (C_MUL, (S_PREV, 0, 0), (S_Y, 0, 0), None), (C_ADD, (S_INTER, 2, 0), (S_INTER, 1, 0), None)]
+    rotations = [0, 3, -5]
+    z = O.fr_from_int(0)
+    e = np.zeros((0, 4), np.uint64)
+    exp_vals = O.graph_evaluate(prog, e, rotations, [cols[2]], [cols[0], cols[1]], [], e, z, z, z, yv, None, prev.copy(), log_size, 4)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).cuda()
+    g = ctx.graph(prog, e, rotations)
+    vals = dev(prev)
+    first, cnt = zk.shard_range(size, rank, world)
+    torch.cuda.synchronize()
+    g.evaluate(vals, log_size, 4, fixed=[dev(cols[2])], advice=[dev(cols[0]), dev(cols[1])], y=yv, rows=(first, cnt))
+    ctx.synchronize()
+    mine = vals.cpu().numpy().view(np.uint64)
+    ok &= bool(np.array_equal(mine[first:first + cnt], exp_vals[first:first + cnt]))
+    other = np.ones(size, bool)
+    other[first:first + cnt] = False
+    ok &= bool(np.array_equal(mine[other], prev[other]))  # rows of other ranks untouched
+    ctx.allgather_rows(vals, log_size)
+    ctx.synchronize()
+    ok &= bool(np.array_equal(vals.cpu().numpy().view(np.uint64), exp_vals))
     q.put((rank, ok))
     dist.barrier()
     srs.release()
@@ -95,3 +126,34 @@ def test_sharded_entry_points_degenerate_on_one_rank(ctx, zk):
     with pytest.raises(zk.B200zkError):
         srs.msm_range(scal[:10], n - 5)  # range runs past the bases
     srs.release()
+
+
+def test_graph_evaluate_rows_in_slices_equals_the_full_evaluation(ctx, zk):
+    """b200zk_graph_evaluate_rows over three ragged row slices (one GPU) == b200zk_graph_evaluate == the oracle; b200zk_allgather_rows
+    is a no-op without a communicator; a slice past the domain is rejected."""
+    import torch
+
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from quotient_programs import C_ADD, C_MUL, S_ADVICE, S_INTER, S_PREV, S_X
+
+    log_size, size = 11, 1 << 11
+    cols = [O.fill_fr(size, 700 + i) for i in range(2)]
+    prev = O.fill_fr(size, 710)
+    prog = [(C_MUL, (S_ADVICE, 0, 1), (S_ADVICE, 1, 0), None), (C_ADD, (S_INTER, 0, 0), (S_X, 0, 0), None), (C_ADD, (S_INTER, 1, 0), (S_PREV, 0, 0), None)]
+    rotations = [0, -7]
+    z, e = O.fr_from_int(0), np.zeros((0, 4), np.uint64)
+    w = O.fr_from_int(pow(zk._ROOT_OF_UNITY, 1 << (28 - log_size), zk.R_MOD))
+    exp = O.graph_evaluate(prog, e, rotations, [], cols, [], e, z, z, z, z, w, prev.copy(), log_size, 2)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).cuda()
+    g = ctx.graph(prog, e, rotations)
+    dcols = [dev(c) for c in cols]
+    vals = dev(prev)
+    torch.cuda.synchronize()
+    for first, cnt in ((0, 700), (700, 1), (701, size - 701)):
+        g.evaluate(vals, log_size, 2, advice=dcols, extended_omega=w, rows=(first, cnt))
+    ctx.allgather_rows(vals, log_size)
+    ctx.synchronize()
+    assert np.array_equal(vals.cpu().numpy().view(np.uint64), exp)
+    with pytest.raises(zk.B200zkError):
+        g.evaluate(vals, log_size, 2, advice=dcols, extended_omega=w, rows=(size - 3, 4))
