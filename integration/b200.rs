@@ -109,3 +109,35 @@ pub(crate) fn run_column_jobs(jobs: &[sys::ColumnJob], k: u32, omega_inv: Fr, ex
     });
     commits
 }
+
+/// The commitments of many columns over one SRS in one batched Pippenger pipeline (b200zk_msm_g1_batch): the advice
+/// phase of a wide circuit (the inner proof's several hundred 2^20-row columns).
+pub(crate) fn commit_batch(srs: *const sys::Srs, columns: &[&[Fr]]) -> Vec<G1> {
+    let n = columns.first().map_or(0, |c| c.len());
+    assert!(columns.iter().all(|c| c.len() == n));
+    let ptrs: Vec<*const c_void> = columns.iter().map(|c| c.as_ptr() as *const c_void).collect();
+    let mut out = vec![G1::default(); columns.len()];
+    check(unsafe { sys::b200zk_msm_g1_batch(ctx(), srs, ptrs.as_ptr(), ptrs.len() as u32, n as u64, out.as_mut_ptr() as _) });
+    out
+}
+
+/// Multi-GPU (one prover process per GPU): join the context-owned NCCL communicator.  Rank 0 obtains `id` with
+/// `comm_unique_id()` and ships the 128 bytes to the other processes over the channel they already share.
+pub(crate) fn comm_unique_id() -> [u8; 128] {
+    let mut id = [0u8; 128];
+    assert_eq!(unsafe { sys::b200zk_comm_unique_id(id.as_mut_ptr() as _) }, sys::OK, "b200zk: NCCL not available");
+    id
+}
+pub(crate) fn comm_init(id: &[u8; 128], rank: usize, world: usize) {
+    check(unsafe { sys::b200zk_ctx_comm_init(ctx(), id.as_ptr() as _, rank as c_int, world as c_int) });
+}
+/// best_multiexp over `values` SHARDED BY POINT RANGE across the ranks (collective: every rank calls it with the same
+/// polynomial; each uploads only its slice); the same normalised point comes back on every rank.
+pub(crate) fn commit_sharded(srs: *const sys::Srs, values: &[Fr], rank: usize, world: usize) -> G1 {
+    let (mut first, mut count) = (0u64, 0u64);
+    check(unsafe { sys::b200zk_shard_range(values.len() as u64, rank as c_int, world as c_int, &mut first, &mut count) });
+    let slice = &values[first as usize..(first + count) as usize];
+    let mut out = G1::default();
+    check(unsafe { sys::b200zk_msm_g1_sharded(ctx(), srs, slice.as_ptr() as _, values.len() as u64, &mut out as *mut G1 as _) });
+    out
+}

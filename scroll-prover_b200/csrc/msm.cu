@@ -394,39 +394,27 @@ __global__ void __launch_bounds__(128) msm_combine_final(const uint32_t* __restr
 //   S = WS(Col) + 2^kc * WS(Row) + sum(Row),     WS(V) = sum_j j V_j = sum_{j>=1} Suffix_j(V)   (parallel suffix scan).
 static constexpr int RED_T = 128;   // 4 blocks/SM at 128 registers: the sums are latency-bound, more blocks in flight win
 
-// XYZZ sum over the lanes of a warp with register shuffles (32 x SHFL.DOWN per level, no shared-memory round trip, no block
-// barrier): after the call lane 0 holds the sum of the first `width` lanes (width a power of two <= 32).
-__device__ __forceinline__ void warp_xyzz_sum(XYZZ& v, int width = 32) {
-    Fq* f = &v.x;
-    for (int off = width >> 1; off > 0; off >>= 1) {
-        XYZZ o;
-        Fq* g = &o.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[k].l.v[j] = __shfl_down_sync(0xffffffffu, f[k].l.v[j], off);
-        xyzz_add(v, o);
-    }
-}
-
-// block sum: warp-shuffle reductions, one shared-memory hand-over between the warps.  Result valid in thread 0.
-// blockDim.x must be a multiple of 32 with a power-of-two number of warps (RED_T = 128: 4 warps).
-__device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {
-    warp_xyzz_sum(v);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (lane == 0) st_xyzz(sh + warp, v);
+// block tree sum through shared memory (result valid in thread 0).  A register-shuffle version (32 x SHFL.DOWN per level and
+// lane, one shared-memory hand-over between the warps) was measured on the B200 and is SLOWER: bucket reduction of 2^21 buckets
+// 2.92 ms against 2.10 ms with this one -- every lane of a shuffle level executes the 14-multiplication addition (31 of 32
+// results are discarded at the last level) and the extra live XYZZ pushed the kernels into spills at 128 registers.
+__device__ __forceinline__ void block_tree_sum(XYZZ& v, XYZZ* sh) {  // result valid in thread 0
+    st_xyzz(sh + threadIdx.x, v);
     __syncthreads();
-    if (warp == 0) {
-        XYZZ t = lane < nwarps ? ld_xyzz(sh + lane) : XYZZ::identity();
-        warp_xyzz_sum(t, (int)nwarps);
-        v = t;
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            XYZZ a = ld_xyzz(sh + threadIdx.x), b = ld_xyzz(sh + threadIdx.x + s);
+            xyzz_add(a, b);
+            st_xyzz(sh + threadIdx.x, a);
+        }
+        __syncthreads();
     }
-    __syncthreads();  // sh may be reused by the caller
+    v = ld_xyzz(sh);
 }
 
 // grid = (rows + cols, Ws); block j < rows sums row j, block rows + j sums column j.  vec[set][0..rows) | [rows..rows+cols)
 __global__ void __launch_bounds__(RED_T, 4) msm_rowcol_sums(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t kc, XYZZ* __restrict__ vec) {
-    __shared__ XYZZ sh[RED_T / 32];  // one slot per warp (block_tree_sum)
+    __shared__ XYZZ sh[RED_T];
     const uint32_t cols = 1u << kc, rows = B >> kc;
     const XYZZ* bk = buckets + (uint64_t)blockIdx.y * B;
     XYZZ acc = XYZZ::identity();
@@ -454,7 +442,7 @@ __global__ void __launch_bounds__(RED_T, 4) msm_rowcol_sums(const XYZZ* __restri
 // blockIdx.x == q_max of the Row vector computes its plain total sum(Row).  out[set][which][b], stride (q_max + 1).
 __global__ void __launch_bounds__(RED_T, 4) msm_bit_sums(const XYZZ* __restrict__ vec, uint32_t B, uint32_t kc, uint32_t q_max,
                                                          XYZZ* __restrict__ out) {
-    __shared__ XYZZ sh[RED_T / 32];  // one slot per warp (block_tree_sum)
+    __shared__ XYZZ sh[RED_T];
     const uint32_t cols = 1u << kc, rows = B >> kc;
     const uint32_t which = blockIdx.y, b = blockIdx.x;
     const uint32_t m = which == 0 ? rows : cols;
@@ -490,7 +478,7 @@ __global__ void __launch_bounds__(64) msm_finish(MsmPlan pl, uint32_t kc, uint32
             uint32_t q = 0;
             while ((1u << q) < m) ++q;
             for (uint32_t b = q; b-- > 0;) {
-                h = xyzz_dbl(h);
+                if (!h.is_identity()) h = xyzz_dbl(h);
                 XYZZ e = ld_xyzz(bv + b);
                 xyzz_add(h, e);
             }
@@ -498,7 +486,8 @@ __global__ void __launch_bounds__(64) msm_finish(MsmPlan pl, uint32_t kc, uint32
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);   // no-op while acc is the identity (Ws == 1)
+            if (!acc.is_identity())                                    // (always the identity when Ws == 1: skip the c doublings)
+                for (uint32_t d = 0; d < pl.c; ++d) acc = xyzz_dbl(acc);
             XYZZ s = ld_xyzz(ws);                                      // WS(Row)
             for (uint32_t d = 0; d < kc; ++d) s = xyzz_dbl(s);
             XYZZ t = ld_xyzz(bits + q_max), u = ld_xyzz(ws + 1);       // sum(Row), WS(Col)
