@@ -72,16 +72,20 @@ def test_shard_range_partitions():
 
 
 def test_job_fanout_is_balanced_and_complete():
+    """bench.py --gpus N: every layer of the chunk step is fanned out on its own (the layers run in sequence)"""
     sys.path.insert(0, ROOT)
     import bench
 
-    jobs = bench.make_jobs()
-    assert sum(1 for j in jobs if j[0] in ("lmsm", "msm")) == 35 and sum(1 for j in jobs if j[0] == "ntt") == 28
-    for world in (1, 2, 4, 8):
-        parts = bench.assign_jobs(jobs, world)
-        assert sum(len(p) for p in parts) == len(jobs)
-        loads = [sum(j[2] for j in p) for p in parts]
-        assert max(loads) <= sum(loads) / world + 44.0  # within one job of perfect balance
+    for layer in bench.CHUNK_LAYERS:
+        jobs = bench.make_jobs(layer)
+        n_msm, n_ntt = layer.wit + layer.uni + layer.coeff, layer.wit + layer.uni
+        assert sum(1 for j in jobs if j[0] in ("lmsm", "msm")) == n_msm and sum(1 for j in jobs if j[0] == "ntt") == n_ntt
+        biggest = max(j[2] for j in jobs)
+        for world in (1, 2, 4, 8):
+            parts = bench.assign_jobs(jobs, world)
+            assert sum(len(p) for p in parts) == len(jobs)
+            loads = [sum(j[2] for j in p) for p in parts]
+            assert max(loads) <= sum(loads) / world + biggest  # within one job of perfect balance
 
 
 def test_shard_ranges_partition_and_lpt_balances():
