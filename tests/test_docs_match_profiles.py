@@ -58,7 +58,15 @@ def test_round2_numbers_quoted_in_design_and_readme():
     DESIGN, README = _doc("DESIGN.md"), _doc("README.md")
     v = bench("bench_r02_v1.json")
     assert "configs[2]" in v["config"]["workload"] and [l["k"] for l in v["config"]["layers"]] == [20, 24, 25]
-    assert f"{v['value']:.3f} s" in DESIGN and f"{v['e2e']['value']:.3f} s" in DESIGN and f"{v['value']:.2f} s" in README
+    assert f"{v['value']:.3f} s" in DESIGN and f"{v['e2e']['value']:.3f} s" in DESIGN
+    v2 = bench("bench_r02_v2.json")  # the final library of the round
+    assert f"{v2['value']:.3f} s" in DESIGN and f"{v2['e2e']['value']:.3f} s" in DESIGN and f"{v2['value']:.2f} s" in README
+    assert v2["clocks"]["reasons"] == [] and v2["gpu_launches"] > 0 and 0.85 < v2["roofline"]["frac"] < 1.0
+    ref = bench("bench_r02_reference_arm.json")
+    assert ref["impl"] == "reference" and ref["extrapolated_by_op_counts"] and ref["full_size_samples"] == len(ref["sample_values_s"]) == 2
+    assert f"{ref['value']:.1f} s" in DESIGN and f"{ref['value']:.0f} s" in README
+    total = sum(ref["cpu_baseline"]["detail"][n]["layer_s"] for n in ("inner", "layer1", "layer2"))
+    assert abs(total - ref["sample_values_s"][-1]) < 1e-6 * total  # detail x op counts reproduces the value
     for name in ("inner", "layer1", "layer2"):
         assert f"{v['layers_s'][name]:.3f}" in DESIGN, name
     assert v["clocks"]["reasons"] == [] and v["clocks"]["sm_mhz"] == 1965 and v["gpu_launches"] > 0
