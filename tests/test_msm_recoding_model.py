@@ -68,3 +68,51 @@ def test_bucket_method_identity_on_a_toy_group(c):
         col = [sum(bw[h * cols + l] for h in range(rows)) % q for l in range(cols)]
         s2 = (sum(l * col[l] for l in range(cols)) + (sum(h * row[h] for h in range(rows)) << kc) + sum(row)) % q
         assert s2 == sum(b * buckets[w][b] for b in range(1, B + 1)) % q
+
+
+@pytest.mark.parametrize("c", [2, 3, 5, 13, 17])
+def test_bit_sliced_weighted_sums_and_batched_bucket_sets(c):
+    """msm_bit_sums / msm_finish: WS(V) = sum_j j V_j is folded from the q subset sums S_b = sum_{j: bit b of j} V_j by Horner with
+    doublings (acc = 2 acc + S_b from the top bit down), for the Row and the Col vector of every bucket set; and the batched
+    pipeline's set index col * Ws + w keeps the columns of a batch apart (msm_run_batch)."""
+    qmod = (1 << 61) - 1
+    rng = random.Random(300 + c)
+    B = 1 << (c - 1)
+    kc = c // 2
+    cols, rows = 1 << kc, B >> kc
+
+    def ws_bit_sliced(v):
+        m = len(v)
+        q = 0
+        while (1 << q) < m:
+            q += 1
+        h = 0
+        for b in reversed(range(q)):
+            h = (2 * h + sum(v[j] for j in range(m) if (j >> b) & 1)) % qmod
+        return h
+
+    for _ in range(3):
+        bw = [rng.randrange(qmod) if rng.random() < 0.7 else 0 for _ in range(B)]
+        row = [sum(bw[h * cols + l] for l in range(cols)) % qmod for h in range(rows)]
+        col = [sum(bw[h * cols + l] for h in range(rows)) % qmod for l in range(cols)]
+        assert ws_bit_sliced(row) == sum(j * x for j, x in enumerate(row)) % qmod
+        assert ws_bit_sliced(col) == sum(j * x for j, x in enumerate(col)) % qmod
+        s = (ws_bit_sliced(col) + (ws_bit_sliced(row) << kc) + sum(row)) % qmod
+        assert s == sum((b + 1) * x for b, x in enumerate(bw)) % qmod  # bucket index b holds digit magnitude b + 1
+    # a batch of 3 columns over the same points: one histogram / sort keyed by (col * Ws + w) * B + bucket
+    n, batch = 60, 3
+    W = 254 // c + 1
+    pts = [rng.randrange(qmod) for _ in range(n)]
+    scal = [[rng.randrange(R) for _ in range(n)] for _ in range(batch)]
+    sets = [[0] * B for _ in range(batch * W)]
+    for colj in range(batch):
+        for s, p in zip(scal[colj], pts):
+            for w, d in enumerate(recode(s, c)):
+                if d:
+                    key = colj * W + w
+                    sets[key][abs(d) - 1] = (sets[key][abs(d) - 1] + (p if d > 0 else -p)) % qmod
+    for colj in range(batch):
+        acc = 0
+        for w in reversed(range(W)):
+            acc = ((acc << c) + sum((b + 1) * x for b, x in enumerate(sets[colj * W + w]))) % qmod
+        assert acc == sum(s * p for s, p in zip(scal[colj], pts)) % qmod
