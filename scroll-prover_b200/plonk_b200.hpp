@@ -170,7 +170,7 @@ class Transcript {
   public:
     static constexpr uint8_t PREFIX_CHALLENGE = 0, PREFIX_POINT = 1, PREFIX_SCALAR = 2;
     Transcript() : state_("Halo2-Transcript") {}
-    explicit Transcript(const std::vector<uint8_t>& proof) : state_("Halo2-Transcript"), proof_(proof), reading_(true) {}
+    explicit Transcript(const std::vector<uint8_t>& proof) : state_("Halo2-Transcript"), proof_(proof) {}
 
     void common_scalar(const Fr& s) {
         uint8_t b[33];
@@ -227,7 +227,6 @@ class Transcript {
     Blake2b state_;
     std::vector<uint8_t> proof_;
     size_t pos_ = 0;
-    bool reading_ = false;
 };
 
 // ------------------------------------------------------------------------------------------------ plonk::Expression
@@ -780,8 +779,8 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     std::vector<Poly> instance_polys, instance_cosets;
     for (auto& inst : instances) {
         if (inst.size() != n) throw Panic("create_proof: instance column length");
-        for (uint64_t r = 0; r + bf + 1 < n; ++r)
-            if (!f_is_zero(inst[r]) || r == 0) { /* upstream hashes exactly the supplied values */ }
+        for (uint64_t r = u; r < n; ++r)
+            if (!f_is_zero(inst[r])) throw Panic("create_proof: instance values beyond the usable rows");
         instance_polys.push_back(ops.lagrange_to_coeff(inst));
         instance_cosets.push_back(ops.coeff_to_extended(instance_polys.back()));
     }
