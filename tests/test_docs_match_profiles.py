@@ -61,7 +61,10 @@ def test_round2_numbers_quoted_in_design_and_readme():
     assert "configs[2]" in v["config"]["workload"] and [l["k"] for l in v["config"]["layers"]] == [20, 24, 25]
     assert f"{v['value']:.3f} s" in DESIGN and f"{v['e2e']['value']:.3f} s" in DESIGN
     v2 = bench("bench_r02_v2.json")  # the final library of the round
-    assert f"{v2['value']:.3f} s" in DESIGN and f"{v2['e2e']['value']:.3f} s" in DESIGN and f"{v2['value']:.2f} s" in README
+    assert f"{v2['value']:.3f} s" in DESIGN and f"{v2['e2e']['value']:.3f} s" in DESIGN
+    v3 = bench("bench_r02_v3.json")  # the final library, bounded in-line CPU sample
+    assert f"{v3['value']:.3f} s" in DESIGN and f"{v3['e2e']['value']:.3f} s" in DESIGN and f"{v3['value']:.2f} s" in README
+    assert v3["cpu_baseline"]["scaled_layers"] == ["layer2"] and abs(v3["cpu_baseline"]["value"] / v2["cpu_baseline"]["value"] - 1) < 0.05
     assert v2["clocks"]["reasons"] == [] and v2["gpu_launches"] > 0 and 0.85 < v2["roofline"]["frac"] < 1.0
     ref = bench("bench_r02_reference_arm.json")
     assert ref["impl"] == "reference" and ref["extrapolated_by_op_counts"] and ref["full_size_samples"] == len(ref["sample_values_s"]) == 2
