@@ -102,6 +102,74 @@ static Circuit build(uint32_t k, uint64_t seed, int sabotage) {
     return C;
 }
 
+// Variant 2 ("wide"): no instance column; 4 advice columns; TWO lookups, one of them with a two-term input compressed with theta
+// against a two-column table; 7 permutation columns (three sets); a query at rotation -1; a cubic gate.
+// fixed: 0 q_a (cubic gate), 1 q_prev (rotation -1 gate), 2 q_l1, 3 t1, 4 q_l2, 5 t2a, 6 t2b, 7 const_a, 8 const_b, 9 const_c
+static Circuit build_wide(uint32_t k, uint64_t seed, int sabotage) {
+    Circuit C;
+    const uint64_t n = 1ull << k;
+    ConstraintSystem& cs = C.cs;
+    cs.num_fixed = 10;
+    cs.num_advice = 4;
+    cs.num_instance = 0;
+    auto a = Expr::advice(0), b = Expr::advice(1), c = Expr::advice(2), d = Expr::advice(3);
+    cs.gates.push_back(Expr::mul(Expr::fixed(0), Expr::sub(Expr::mul(Expr::mul(a, b), c), d)));            // q_a (a b c - d): degree 4
+    cs.gates.push_back(Expr::mul(Expr::fixed(1), Expr::sub(Expr::sum(Expr::advice(3, -1), a), b)));         // q_prev (d(omega^-1 X) + a - b)
+    Lookup l1, l2;
+    l1.inputs = {Expr::mul(Expr::fixed(2), c)};
+    l1.table = {Expr::fixed(3)};
+    l2.inputs = {Expr::mul(Expr::fixed(4), a), Expr::mul(Expr::fixed(4), b)};                                // (q a, q b) in (t2a, t2b)
+    l2.table = {Expr::fixed(5), Expr::fixed(6)};
+    cs.lookups = {l1, l2};
+    cs.permutation = {{Expr::Advice, 0}, {Expr::Advice, 1}, {Expr::Advice, 2}, {Expr::Advice, 3}, {Expr::Fixed, 7}, {Expr::Fixed, 8}, {Expr::Fixed, 9}};
+    cs.finalize();
+    const uint32_t bf = cs.blinding_factors();
+    const uint64_t u = n - bf - 1;
+    C.fixed.assign(10, Poly(n, f_zero()));
+    C.advice.assign(4, Poly(n, f_zero()));
+    C.assembly.reset(new Assembly(7, n));
+    Rng rng(seed * 131 + 9);
+    for (uint64_t r = 0; r < u; ++r) {
+        C.fixed[3][r] = f_u64(3 * r);                     // table 1: multiples of 3 (contains 0)
+        C.fixed[5][r] = f_u64(r);                         // table 2: pairs (r, r^2 + 1) ... and (0, 0) at the disabled rows' target
+        C.fixed[6][r] = r == 0 ? f_zero() : f_u64(r * r + 1);
+    }
+    C.fixed[7][2] = f_u64(11);
+    C.fixed[8][3] = f_u64(12);
+    C.fixed[9][4] = f_u64(13);
+    for (uint64_t r = 0; r < u; ++r) {
+        const bool l1_row = (r % 4 == 1), l2_row = (r % 4 == 2), prev_row = (r % 7 == 5) && !l2_row;
+        Fr av = rng.fr(), bv = rng.fr(), cv = rng.fr();
+        if (l1_row) cv = f_u64(3 * (rng.next() % u));
+        if (l2_row) {
+            uint64_t t = 1 + rng.next() % (u - 1);
+            av = f_u64(t);
+            bv = f_u64(t * t + 1);
+        }
+        if (r == 8) av = f_u64(11);  // the cells the three constants are copied into (rows free of lookups and of q_prev)
+        if (r == 3) bv = f_u64(12);
+        if (r == 4) cv = f_u64(13);
+        if (prev_row) bv = f_add(C.advice[3][r - 1], av);  // q_prev: b = d[r-1] + a
+        C.advice[0][r] = av;
+        C.advice[1][r] = bv;
+        C.advice[2][r] = cv;
+        C.advice[3][r] = f_mul(f_mul(av, bv), cv);
+        C.fixed[0][r] = f_one();
+        if (prev_row) C.fixed[1][r] = f_one();
+        if (l1_row) C.fixed[2][r] = f_one();
+        if (l2_row) C.fixed[4][r] = f_one();
+    }
+    C.assembly->copy(4, 2, 0, 8);   // const_a[2] = a[8]
+    C.assembly->copy(5, 3, 1, 3);   // const_b[3] = b[3]
+    C.assembly->copy(6, 4, 2, 4);   // const_c[4] = c[4]
+    C.assembly->copy(3, 5, 3, 5);   // a cell copied onto itself: no-op
+    if (sabotage == 1) C.advice[3][6] = f_add(C.advice[3][6], f_one());   // breaks the cubic gate only
+    if (sabotage == 2) C.advice[1][3] = f_add(C.advice[1][3], f_one());   // breaks the copy of const_b (and gates)
+    if (sabotage == 3) C.advice[1][2] = f_add(C.advice[1][2], f_one());   // lookup 2: (a, b) no longer a row of the two-column table
+    if (sabotage == 4) C.advice[2][5] = f_u64(3 * u + 1);                 // lookup 1 row 5: value outside table 1
+    return C;
+}
+
 static std::string hex(const std::vector<uint8_t>& v) {
     static const char* d = "0123456789abcdef";
     std::string s;
@@ -131,10 +199,13 @@ int main(int argc, char** argv) {
     }
     const uint32_t k = argc > 2 ? (uint32_t)std::atoi(argv[2]) : 6;
     const uint64_t seed = argc > 3 ? (uint64_t)std::atoll(argv[3]) : 1;
+    const int variant = argc > 4 ? std::atoi(argv[4]) : 1;
     const uint64_t n = 1ull << k;
+    auto build_any = [&](int sabotage) { return variant == 2 ? build_wide(k, seed, sabotage) : build(k, seed, sabotage); };
     try {
-        Circuit C = build(k, seed, 0);
-        REQUIRE(C.cs.degree() == 5 && C.cs.blinding_factors() == 5 && C.cs.permutation_chunk_len() == 3);
+        Circuit C = build_any(0);
+        if (variant == 1) REQUIRE(C.cs.degree() == 5 && C.cs.blinding_factors() == 5 && C.cs.permutation_chunk_len() == 3);
+        if (variant == 2) REQUIRE(C.cs.degree() == 5 && C.cs.permutation_chunk_len() == 3 && C.cs.lookups.size() == 2 && C.cs.permutation.size() == 7);
         EvaluationDomain dom = EvaluationDomain::new_(C.cs.degree(), k);
         REQUIRE(dom.extended_k == k + 2 && dom.quotient_poly_degree == 4);
 
@@ -158,6 +229,7 @@ int main(int argc, char** argv) {
         ProofArtifacts po = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB200 + seed);
         std::printf("proof_bytes %zu commitments %zu evals %zu\n", po.proof.size(), po.n_commitments, po.n_evals);
         REQUIRE(po.proof.size() == 32 * (po.n_commitments + po.n_evals));
+        if (variant == 2) REQUIRE(po.n_commitments == 4 + 2 + 3 + 2 + 1 + 4 + 2);  // advice, m x2, z x3, phi x2, random, h x4, SHPLONK x2
         std::printf("proof_sha_input oracle %s\n", hex(po.proof).c_str());
         std::string why;
         if (!verify_proof(dom, pk_o.vk, vp, C.instances, po.proof, &why)) std::printf("verify_proof rejected the honest proof: %s\n", why.c_str());
@@ -170,9 +242,11 @@ int main(int argc, char** argv) {
             REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, bad, &why));
         }
         {
-            std::vector<Poly> wrong = C.instances;
-            wrong[0][0] = f_add(wrong[0][0], f_one());
-            REQUIRE(!verify_proof(dom, pk_o.vk, vp, wrong, po.proof, &why));
+            if (!C.instances.empty()) {
+                std::vector<Poly> wrong = C.instances;
+                wrong[0][0] = f_add(wrong[0][0], f_one());
+                REQUIRE(!verify_proof(dom, pk_o.vk, vp, wrong, po.proof, &why));
+            }
             std::vector<uint8_t> shorter(po.proof.begin(), po.proof.end() - 32), longer = po.proof;
             longer.push_back(0);
             REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, shorter, &why) && !verify_proof(dom, pk_o.vk, vp, C.instances, longer, &why));
@@ -183,7 +257,7 @@ int main(int argc, char** argv) {
         }
         // ---- unsatisfied witnesses: the prover either refuses (copy / lookup checks) or its proof is rejected (gates)
         for (int sabotage = 1; sabotage <= 4; ++sabotage) {
-            Circuit B = build(k, seed, sabotage);
+            Circuit B = build_any(sabotage);
             bool accepted = false;
             try {
                 ProofArtifacts pb = create_proof(oops, dom, pk_o, B.advice, B.instances, 0xB200 + seed);

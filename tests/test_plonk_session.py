@@ -17,7 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_plonk_session.cpp")
 BIN = os.path.join(ROOT, "tests", "cpp", "test_plonk_session")
 DIGESTS = os.path.join(ROOT, "tests", "golden", "plonk_session_digests.json")
-CASES = [(6, 1), (7, 3)]
+CASES = [(6, 1, 1), (7, 3, 1), (6, 1, 2), (7, 4, 2)]  # (k, seed, circuit variant: 1 = instance + one lookup + two permutation sets,
+#                                                          2 = "wide": two lookups (one two-column), three permutation sets, rotation -1)
+SHAPE = {1: "proof_bytes 1216 commitments 14 evals 24", 2: "proof_bytes 1760 commitments 18 evals 37"}
 
 
 def binary():
@@ -31,8 +33,8 @@ def binary():
     return BIN
 
 
-def run(mode, k, seed):
-    r = subprocess.run([binary(), mode, str(k), str(seed)], capture_output=True, text=True, timeout=900)
+def run(mode, k, seed, variant=1):
+    r = subprocess.run([binary(), mode, str(k), str(seed), str(variant)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-2000:] + r.stderr[-2000:]
     proofs = {l.split()[1]: bytes.fromhex(l.split()[2]) for l in r.stdout.splitlines() if l.startswith("proof_sha_input")}
     return proofs, r.stdout
@@ -44,21 +46,24 @@ def test_blake2b_transcript_hash_matches_hashlib():
         assert out == hashlib.blake2b(msg, digest_size=64, person=b"Halo2-Transcript").hexdigest()
 
 
-@pytest.mark.parametrize("k,seed", CASES)
-def test_session_over_the_oracle_verifies_and_matches_the_committed_digest(k, seed):
-    proofs, out = run("oracle", k, seed)
-    assert "proof_bytes 1216 commitments 14 evals 24" in out  # 3 advice + m + 2 z + phi + random + 4 h + 2 SHPLONK points
-    want = json.load(open(DIGESTS))[f"k{k}_seed{seed}"]
+def key(k, seed, variant):
+    return f"k{k}_seed{seed}" + ("" if variant == 1 else f"_v{variant}")
+
+
+@pytest.mark.parametrize("k,seed,variant", CASES)
+def test_session_over_the_oracle_verifies_and_matches_the_committed_digest(k, seed, variant):
+    proofs, out = run("oracle", k, seed, variant)
+    assert SHAPE[variant] in out  # variant 1: 3 advice + m + 2 z + phi + random + 4 h + 2 SHPLONK points
+    want = json.load(open(DIGESTS))[key(k, seed, variant)]
     assert hashlib.sha256(proofs["oracle"]).hexdigest() == want
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,seed", CASES + [(9, 5)])
-def test_session_on_the_device_gives_identical_proof_bytes(k, seed):
-    proofs, out = run("both", k, seed)
+@pytest.mark.parametrize("k,seed,variant", CASES + [(9, 5, 1), (8, 2, 2)])
+def test_session_on_the_device_gives_identical_proof_bytes(k, seed, variant):
+    proofs, out = run("both", k, seed, variant)
     assert "device proof identical to the oracle's" in out
     assert proofs["device"] == proofs["oracle"]
-    key = f"k{k}_seed{seed}"
     digests = json.load(open(DIGESTS))
-    if key in digests:
-        assert hashlib.sha256(proofs["device"]).hexdigest() == digests[key]
+    if key(k, seed, variant) in digests:
+        assert hashlib.sha256(proofs["device"]).hexdigest() == digests[key(k, seed, variant)]
