@@ -979,9 +979,9 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     const Fr sy = tr.squeeze_challenge();  // y of the multiopen argument
     const Fr sv = tr.squeeze_challenge();  // v
     RotationSets rs = build_rotation_sets(queries);
-    std::vector<Poly> set_numerators;      // per set: sum_j y^j (p_j(X) - r_j(X)) with fold(acc * y + p)
+    std::vector<Poly> set_numerators;      // per set: sum_j y^j (p_j(X) - r_j(X)), ascending powers in query order
     std::vector<std::vector<Poly>> set_r;  // r_j(X) per set and polynomial
-    Poly h_open;                           // sum over sets, fold(acc * v + quotient_set)
+    Poly h_open;                           // sum_i v^i quotient_set_i, ascending powers in set order
     {
         std::vector<Poly> quotients;
         for (auto& set : rs.sets) {
@@ -996,7 +996,7 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
             std::vector<const Poly*> ps;
             std::vector<Fr> sc(diffs.size());
             Fr p = f_one();
-            for (size_t j = diffs.size(); j-- > 0;) { sc[j] = p; p = f_mul(p, sy); }  // fold(acc * y + poly): first poly gets the highest power
+            for (size_t j = 0; j < diffs.size(); ++j) { sc[j] = p; p = f_mul(p, sy); }  // numerators.zip(powers(y)): ascending powers, as upstream
             for (auto& d : diffs) ps.push_back(&d);
             Poly num = ops.poly_lincomb(ps, sc);
             Poly q = num;
@@ -1008,7 +1008,7 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
         std::vector<const Poly*> ps;
         std::vector<Fr> sc(quotients.size());
         Fr p = f_one();
-        for (size_t i = quotients.size(); i-- > 0;) { sc[i] = p; p = f_mul(p, sv); }
+        for (size_t i = 0; i < quotients.size(); ++i) { sc[i] = p; p = f_mul(p, sv); }  // .zip(powers(v))
         for (auto& q : quotients) ps.push_back(&q);
         h_open = ops.poly_lincomb(ps, sc);
     }
@@ -1030,13 +1030,13 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
         Fr constant = f_zero();  // the r_ij(u) part, subtracted from the constant coefficient
         Fr vp = f_one();
         std::vector<Fr> vpow(rs.sets.size());
-        for (size_t i = rs.sets.size(); i-- > 0;) { vpow[i] = vp; vp = f_mul(vp, sv); }
+        for (size_t i = 0; i < rs.sets.size(); ++i) { vpow[i] = vp; vp = f_mul(vp, sv); }
         for (size_t i = 0; i < rs.sets.size(); ++i) {
             const Fr w = f_mul(f_mul(vpow[i], z_diff[i]), z0_inv);
             // N_i(X) + sum_j y^(..) r_ij(X)  is  sum_j y^(..) p_ij(X); we need  sum_j y^(..) (p_ij(X) - r_ij(u))
             Fr yp = f_one(), ru = f_zero();
             std::vector<Fr> ypow(set_r[i].size());
-            for (size_t j = set_r[i].size(); j-- > 0;) { ypow[j] = yp; yp = f_mul(yp, sy); }
+            for (size_t j = 0; j < set_r[i].size(); ++j) { ypow[j] = yp; yp = f_mul(yp, sy); }
             for (size_t j = 0; j < set_r[i].size(); ++j) {
                 ps.push_back(open_polys[rs.sets[i].polys[j]]);
                 sc.push_back(f_mul(w, ypow[j]));
@@ -1245,14 +1245,14 @@ inline bool verify_proof(const EvaluationDomain& dom, const VerifyingKey& vk, co
         const Fr z0_inv = f_inv(z_diff[0]);
         std::vector<Fr> vpow(rs.sets.size());
         Fr vacc = f_one();
-        for (size_t i = rs.sets.size(); i-- > 0;) { vpow[i] = vacc; vacc = f_mul(vacc, sv); }
+        for (size_t i = 0; i < rs.sets.size(); ++i) { vpow[i] = vacc; vacc = f_mul(vacc, sv); }  // gamma.powers(sets.len()) of snark-verifier's Bdfg21
         hostg1::XYZZ E = hostg1::XYZZ::identity();
         Fr r_total = f_zero();
         for (size_t i = 0; i < rs.sets.size(); ++i) {
             const Fr w = f_mul(f_mul(vpow[i], z_diff[i]), z0_inv);
             std::vector<Fr> ypow(rs.sets[i].polys.size());
             Fr yp = f_one();
-            for (size_t j = ypow.size(); j-- > 0;) { ypow[j] = yp; yp = f_mul(yp, sy); }
+            for (size_t j = 0; j < ypow.size(); ++j) { ypow[j] = yp; yp = f_mul(yp, sy); }  // mu.powers(..)
             for (size_t j = 0; j < rs.sets[i].polys.size(); ++j) {
                 Poly r = lagrange_interpolate(rs.sets[i].points, rs.sets[i].evals[j]);
                 const Fr s = f_mul(w, ypow[j]);
