@@ -165,14 +165,144 @@ inline serde::G1Point to_affine_point(const G1& j) {  // normalised Jacobian (x,
     return p;
 }
 
-// transcript::{Blake2bWrite, Blake2bRead}<_, G1Affine, Challenge255<_>>
+// ------------------------------------------------------------------------------------------------ Poseidon (snark-verifier's transcript hash)
+// snark-verifier's native transcript for the chunk / batch proofs (`PoseidonTranscript`, system/halo2/transcript/halo2.rs) hashes with
+// the Poseidon sponge of util/hash/poseidon.rs at T = 5, RATE = 4, R_F = 8, R_P = 60; the round constants and the Cauchy MDS matrix
+// come from the Grain LFSR of the Poseidon paper.  tests/test_reference_proofs_kat.py pins these parameters and conventions on the
+// reference's shipped proofs (through the Python model tests/snark_verifier_model.py); this C++ sponge is checked against that model.
+class PoseidonSpec {
+  public:
+    static constexpr int T = 5, RATE = 4, R_F = 8, R_P = 60;
+    std::vector<std::array<DFr, T>> rc;
+    std::array<std::array<DFr, T>, T> mds;
+    static const PoseidonSpec& get() {
+        static const PoseidonSpec s;
+        return s;
+    }
+    void permute(std::array<DFr, T>& st) const {
+        auto pow5 = [](const DFr& x) { DFr x2 = x.sqr(); return x2.sqr() * x; };
+        auto mix = [&](std::array<DFr, T>& s) {
+            std::array<DFr, T> o;
+            for (int i = 0; i < T; ++i) {
+                DFr acc = DFr::zero();
+                for (int j = 0; j < T; ++j) acc = acc + mds[i][j] * s[j];
+                o[i] = acc;
+            }
+            s = o;
+        };
+        size_t r = 0;
+        for (int k = 0; k < R_F / 2; ++k, ++r) {
+            for (int i = 0; i < T; ++i) st[i] = pow5(st[i] + rc[r][i]);
+            mix(st);
+        }
+        for (int k = 0; k < R_P; ++k, ++r) {
+            for (int i = 0; i < T; ++i) st[i] = st[i] + rc[r][i];
+            st[0] = pow5(st[0]);
+            mix(st);
+        }
+        for (int k = 0; k < R_F / 2; ++k, ++r) {
+            for (int i = 0; i < T; ++i) st[i] = pow5(st[i] + rc[r][i]);
+            mix(st);
+        }
+    }
+
+  private:
+    struct Grain {  // generate_parameters_grain: 80-bit LFSR, taps 62 51 38 23 13 0, self-shrinking output
+        std::vector<uint8_t> s;
+        Grain(uint32_t t, uint32_t r_f, uint32_t r_p) {
+            auto put = [&](uint32_t v, int width) { for (int i = width - 1; i >= 0; --i) s.push_back((v >> i) & 1); };
+            put(1, 2); put(0, 4); put(254, 12); put(t, 12); put(r_f, 10); put(r_p, 10); put((1u << 30) - 1, 30);
+            for (int i = 0; i < 160; ++i) update();
+        }
+        uint8_t update() {
+            uint8_t b = s[62] ^ s[51] ^ s[38] ^ s[23] ^ s[13] ^ s[0];
+            s.erase(s.begin());
+            s.push_back(b);
+            return b;
+        }
+        uint8_t bit() {
+            for (;;) {
+                uint8_t first = update(), second = update();
+                if (first) return second;
+            }
+        }
+        void bits254_le(uint8_t out[64]) {  // 254 output bits, most significant first, as a little-endian 64-byte integer
+            std::memset(out, 0, 64);
+            for (int i = 253; i >= 0; --i)
+                if (bit()) out[i / 8] |= (uint8_t)(1u << (i % 8));
+        }
+        Fr element(bool reject) {
+            for (;;) {
+                uint8_t b[64];
+                bits254_le(b);
+                Fr v;
+                if (!reject) return f_from_bytes_wide(b);
+                if (f_from_repr(b, &v)) return v;
+            }
+        }
+    };
+    PoseidonSpec() {
+        Grain g(T, R_F, R_P);
+        rc.resize(R_F + R_P);
+        for (auto& row : rc)
+            for (auto& c : row) c = to_dev(g.element(true));
+        for (;;) {
+            Fr v[2 * T];
+            for (auto& e : v) e = g.element(false);
+            bool distinct = true;
+            for (int i = 0; i < 2 * T; ++i)
+                for (int j = i + 1; j < 2 * T; ++j) distinct &= !(v[i] == v[j]);
+            if (!distinct) continue;
+            for (int i = 0; i < T; ++i)
+                for (int j = 0; j < T; ++j) mds[i][j] = (to_dev(v[i]) + to_dev(v[T + j])).inv();
+            break;
+        }
+    }
+};
+
+// util/hash/poseidon.rs: state [2^64, 0, ..]; update() buffers; squeeze() absorbs the buffer in RATE chunks -- a partial (or empty)
+// last chunk is followed by a one -- and returns state[1]; the state carries over from one squeeze to the next
+class PoseidonSponge {
+  public:
+    PoseidonSponge() {
+        for (auto& x : st_) x = DFr::zero();
+        st_[0] = to_dev(f_pow(f_u64(2), 64));
+    }
+    void update(const Fr& v) { buf_.push_back(to_dev(v)); }
+    Fr squeeze() {
+        std::vector<DFr> buf;
+        buf.swap(buf_);
+        const bool exact = buf.size() % PoseidonSpec::RATE == 0;
+        for (size_t i = 0; i < buf.size(); i += PoseidonSpec::RATE) permutation(buf.data() + i, std::min(buf.size() - i, (size_t)PoseidonSpec::RATE));
+        if (exact) permutation(nullptr, 0);
+        return from_dev(st_[1]);
+    }
+
+  private:
+    void permutation(const DFr* chunk, size_t len) {
+        for (size_t i = 0; i < len; ++i) st_[i + 1] = st_[i + 1] + chunk[i];
+        if (len + 1 < (size_t)PoseidonSpec::T) st_[len + 1] = st_[len + 1] + DFr::one();
+        PoseidonSpec::get().permute(st_);
+    }
+    std::array<DFr, PoseidonSpec::T> st_;
+    std::vector<DFr> buf_;
+};
+
+// transcript::{Blake2bWrite, Blake2bRead}<_, G1Affine, Challenge255<_>> (halo2's default), or snark-verifier's PoseidonTranscript
+// (the one the reference's chunk / batch proofs are made with): same proof bytes layout, different challenge derivation
+enum class TranscriptKind { Blake2b, Poseidon };
 class Transcript {
   public:
     static constexpr uint8_t PREFIX_CHALLENGE = 0, PREFIX_POINT = 1, PREFIX_SCALAR = 2;
-    Transcript() : state_("Halo2-Transcript") {}
-    explicit Transcript(const std::vector<uint8_t>& proof) : state_("Halo2-Transcript"), proof_(proof) {}
+    explicit Transcript(TranscriptKind kind = TranscriptKind::Blake2b) : kind_(kind), state_("Halo2-Transcript") {}
+    explicit Transcript(const std::vector<uint8_t>& proof, TranscriptKind kind = TranscriptKind::Blake2b)
+        : kind_(kind), state_("Halo2-Transcript"), proof_(proof) {}
 
     void common_scalar(const Fr& s) {
+        if (kind_ == TranscriptKind::Poseidon) {
+            sponge_.update(s);
+            return;
+        }
         uint8_t b[33];
         b[0] = PREFIX_SCALAR;
         f_to_repr(s, b + 1);
@@ -180,6 +310,14 @@ class Transcript {
     }
     void common_point(const serde::G1Point& p) {  // coordinates, little-endian canonical (x then y)
         if (p.x.is_zero() && p.y.is_zero()) throw Panic("cannot write points at infinity to the transcript");
+        if (kind_ == TranscriptKind::Poseidon) {  // fe_to_fe::<Fq, Fr>: the coordinates reduced into the scalar field
+            uint8_t w[64] = {0};
+            serde::fq_to_le32(p.x, w);
+            sponge_.update(f_from_bytes_wide(w));
+            serde::fq_to_le32(p.y, w);
+            sponge_.update(f_from_bytes_wide(w));
+            return;
+        }
         uint8_t b[65];
         b[0] = PREFIX_POINT;
         serde::fq_to_le32(p.x, b + 1);
@@ -216,6 +354,7 @@ class Transcript {
         return s;
     }
     Fr squeeze_challenge() {
+        if (kind_ == TranscriptKind::Poseidon) return sponge_.squeeze();
         state_.update(&PREFIX_CHALLENGE, 1);
         auto h = state_.finalize();
         return f_from_bytes_wide(h.data());
@@ -224,7 +363,9 @@ class Transcript {
     bool exhausted() const { return pos_ == proof_.size(); }
 
   private:
+    TranscriptKind kind_;
     Blake2b state_;
+    PoseidonSponge sponge_;
     std::vector<uint8_t> proof_;
     size_t pos_ = 0;
 };
@@ -762,7 +903,8 @@ struct ProofArtifacts {  // what a caller may want beside the bytes (tests)
 // plonk::create_proof for one circuit instance with one phase.  advice: Lagrange values of every advice column (usable rows
 // filled by the caller's synthesis; the blinding rows are overwritten here), instances: Lagrange values of the instance columns.
 inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const ProvingKey& pk, std::vector<Poly> advice,
-                                   const std::vector<Poly>& instances, uint64_t rng_seed) {
+                                   const std::vector<Poly>& instances, uint64_t rng_seed,
+                                   TranscriptKind transcript_kind = TranscriptKind::Blake2b) {
     const ConstraintSystem& cs = pk.vk.cs;
     const uint64_t n = dom.n;
     const uint32_t bf = cs.blinding_factors();
@@ -770,7 +912,7 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     const AuxLayout aux = aux_layout(cs);
     if (advice.size() != cs.num_advice || instances.size() != cs.num_instance) throw Panic("create_proof: wrong number of columns");
     Rng rng(rng_seed);
-    Transcript tr;
+    Transcript tr(transcript_kind);
     ProofArtifacts art;
     auto write_point = [&](const G1& c) { tr.write_point(c); art.n_commitments++; };
 
@@ -1055,6 +1197,136 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     return art;
 }
 
+// ------------------------------------------------------------------------------------------------ snark-verifier protocol export
+// What snark-verifier's `compile(params, vk, config)` (system/halo2.rs) produces for a halo2 verifying key, written for OUR key in the
+// serde_json schema of the reference's `*.protocol` files (protocol_json.hpp reads it back): polynomial indices = preprocessed (fixed,
+// then permutation commitments) | instance columns | witnesses in commitment order (advice, lookup m, permutation z, lookup phi,
+// random) | quotient; the evaluations in the order create_proof writes them; the opening queries in the order the SHPLONK prover
+// takes them; the quotient numerator as an expression tree folded with the last challenge.  A proof made by create_proof with
+// TranscriptKind::Poseidon verifies under a verifier that is driven by this JSON alone -- tests/snark_verifier_model.py, the model
+// that accepts the reference's shipped chunk and batch proofs.
+inline std::string export_protocol_json(const EvaluationDomain& dom, const VerifyingKey& vk) {
+    const ConstraintSystem& cs = vk.cs;
+    const uint32_t bf = cs.blinding_factors();
+    const uint64_t u = dom.n - bf - 1;
+    const AuxLayout aux = aux_layout(cs);
+    const size_t n_pre = vk.fixed_commitments.size() + vk.permutation_commitments.size(), n_inst = cs.num_instance;
+    const size_t A = cs.num_advice, L = cs.lookups.size(), S = aux.n_sets;
+    const size_t w0 = n_pre + n_inst, p_m = w0 + A, p_z = p_m + L, p_phi = p_z + S, p_random = p_phi + L, p_quotient = p_random + 1;
+    auto limbs = [](const uint64_t l[4]) {
+        return "[" + std::to_string(l[0]) + ", " + std::to_string(l[1]) + ", " + std::to_string(l[2]) + ", " + std::to_string(l[3]) + "]";
+    };
+    auto fr = [&](const Fr& v) { return limbs(v.l); };
+    auto fq = [&](const b200zk::Fq& v) {
+        uint64_t l[4];
+        std::memcpy(l, v.l.v, 32);
+        return limbs(l);
+    };
+    auto poly = [](size_t idx, int32_t rot) { return "{\"Polynomial\": {\"poly\": " + std::to_string(idx) + ", \"rotation\": " + std::to_string(rot) + "}}"; };
+    auto constant = [&](const Fr& v) { return "{\"Constant\": " + fr(v) + "}"; };
+    auto challenge = [](int i) { return "{\"Challenge\": " + std::to_string(i) + "}"; };
+    auto lagrange = [](int64_t i) { return "{\"CommonPolynomial\": {\"Lagrange\": " + std::to_string(i) + "}}"; };
+    const std::string identity = "{\"CommonPolynomial\": \"Identity\"}";
+    auto neg = [](const std::string& a) { return "{\"Negated\": " + a + "}"; };
+    auto sum = [](const std::string& a, const std::string& b) { return "{\"Sum\": [" + a + ", " + b + "]}"; };
+    auto sub = [&](const std::string& a, const std::string& b) { return sum(a, neg(b)); };
+    auto mul = [](const std::string& a, const std::string& b) { return "{\"Product\": [" + a + ", " + b + "]}"; };
+    const std::string theta = challenge(0), beta = challenge(1), gamma = challenge(2), one = constant(f_one());
+    std::function<std::string(const Expr&)> expr = [&](const Expr& e) -> std::string {
+        switch (e.kind) {
+            case Expr::Constant: return constant(e.c);
+            case Expr::Fixed: return poly(e.col, e.rot);
+            case Expr::Advice: return poly(w0 + e.col, e.rot);
+            case Expr::Instance: return poly(n_pre + e.col, e.rot);
+            case Expr::Negated: return neg(expr(*e.a));
+            case Expr::Sum: return sum(expr(*e.a), expr(*e.b));
+            case Expr::Product: return mul(expr(*e.a), expr(*e.b));
+            default: return "{\"Scaled\": [" + expr(*e.a) + ", " + fr(e.c) + "]}";
+        }
+    };
+    auto column = [&](const Column& c) { return c.kind == Expr::Advice ? poly(w0 + c.index, 0) : (c.kind == Expr::Fixed ? poly(c.index, 0) : poly(n_pre + c.index, 0)); };
+    const int32_t last = -(int32_t)(bf + 1);
+    std::string l_blind = lagrange(-1);
+    for (uint32_t i = 2; i <= bf; ++i) l_blind = sum(l_blind, lagrange(-(int64_t)i));
+    const std::string l_0 = lagrange(0), l_last = lagrange(last), l_active = sub(one, sum(l_last, l_blind));
+    std::vector<std::string> terms;
+    for (auto& g : cs.gates) terms.push_back(expr(*g));
+    if (!cs.permutation.empty()) {
+        const uint32_t chunk = cs.permutation_chunk_len();
+        terms.push_back(mul(l_0, sub(one, poly(p_z, 0))));
+        terms.push_back(mul(l_last, sub(mul(poly(p_z + S - 1, 0), poly(p_z + S - 1, 0)), poly(p_z + S - 1, 0))));
+        for (size_t sidx = 1; sidx < S; ++sidx) terms.push_back(mul(l_0, sub(poly(p_z + sidx, 0), poly(p_z + sidx - 1, last))));
+        Fr dpow = f_one();
+        const Fr delta = f_delta();
+        for (size_t sidx = 0; sidx < S; ++sidx) {
+            std::string left = poly(p_z + sidx, 1), right = poly(p_z + sidx, 0);
+            for (size_t i = sidx * chunk; i < std::min(cs.permutation.size(), (sidx + 1) * (size_t)chunk); ++i) {
+                const std::string v = column(cs.permutation[i]);
+                left = mul(left, sum(sum(v, mul(beta, poly(vk.fixed_commitments.size() + i, 0))), gamma));
+                right = mul(right, sum(sum(v, mul(mul(beta, identity), constant(dpow))), gamma));
+                dpow = f_mul(dpow, delta);
+            }
+            terms.push_back(mul(sub(left, right), l_active));
+        }
+    }
+    for (size_t li = 0; li < L; ++li) {
+        auto compress = [&](const std::vector<ExprP>& es) {
+            std::string acc = constant(f_zero());
+            for (auto& e : es) acc = sum(mul(acc, theta), expr(*e));
+            return acc;
+        };
+        const std::string fi = sum(compress(cs.lookups[li].inputs), beta), tau = sum(compress(cs.lookups[li].table), beta);
+        const std::string phi = poly(p_phi + li, 0), phi_next = poly(p_phi + li, 1), m = poly(p_m + li, 0);
+        terms.push_back(mul(l_0, phi));
+        terms.push_back(mul(l_last, phi));
+        terms.push_back(mul(sub(mul(mul(tau, fi), sub(phi_next, phi)), sub(tau, mul(m, fi))), l_active));
+    }
+    // evaluations (write order of create_proof) and queries (order of its SHPLONK opening claims)
+    std::vector<std::pair<size_t, int32_t>> evals, queries, q_fixed, q_sigma;
+    for (auto& q : cs.advice_queries) evals.push_back({w0 + q.first, q.second});
+    for (auto& q : cs.fixed_queries) { evals.push_back({q.first, q.second}); q_fixed.push_back({q.first, q.second}); }
+    evals.push_back({p_random, 0});
+    for (size_t i = 0; i < vk.permutation_commitments.size(); ++i) { evals.push_back({vk.fixed_commitments.size() + i, 0}); q_sigma.push_back({vk.fixed_commitments.size() + i, 0}); }
+    for (auto& q : cs.advice_queries) queries.push_back({w0 + q.first, q.second});
+    for (size_t sidx = 0; sidx < S; ++sidx)
+        for (int32_t rot : {0, 1, last}) {
+            if (rot == last && sidx + 1 == S) continue;
+            evals.push_back({p_z + sidx, rot});
+            queries.push_back({p_z + sidx, rot});
+        }
+    for (size_t li = 0; li < L; ++li)
+        for (auto pr : {std::pair<size_t, int32_t>{p_phi + li, 0}, {p_phi + li, 1}, {p_m + li, 0}}) {
+            evals.push_back(pr);
+            queries.push_back(pr);
+        }
+    queries.insert(queries.end(), q_fixed.begin(), q_fixed.end());
+    queries.insert(queries.end(), q_sigma.begin(), q_sigma.end());
+    queries.push_back({p_quotient, 0});
+    queries.push_back({p_random, 0});
+    auto list = [](const std::vector<std::pair<size_t, int32_t>>& v) {
+        std::string o = "[";
+        for (size_t i = 0; i < v.size(); ++i) o += std::string(i ? ", " : "") + "{\"poly\": " + std::to_string(v[i].first) + ", \"rotation\": " + std::to_string(v[i].second) + "}";
+        return o + "]";
+    };
+    std::string numerator = "{\"DistributePowers\": [[";
+    for (size_t i = 0; i < terms.size(); ++i) numerator += (i ? ", " : "") + terms[i];
+    numerator += "], " + challenge(3) + "]}";
+    std::string pre = "[";
+    size_t cnt = 0;
+    for (auto* v : {&vk.fixed_commitments, &vk.permutation_commitments})
+        for (auto& pt : *v) pre += std::string(cnt++ ? ", " : "") + "{\"x\": " + fq(pt.x) + ", \"y\": " + fq(pt.y) + "}";
+    pre += "]";
+    std::string inst = "[";
+    for (size_t i = 0; i < n_inst; ++i) inst += std::string(i ? ", " : "") + std::to_string(u);
+    inst += "]";
+    return "{\"domain\": {\"k\": " + std::to_string(dom.k) + ", \"n\": " + std::to_string(dom.n) + ", \"n_inv\": " + fr(dom.ifft_divisor) + ", \"gen\": " +
+           fr(dom.omega) + ", \"gen_inv\": " + fr(dom.omega_inv) + "}, \"preprocessed\": " + pre + ", \"num_instance\": " + inst +
+           ", \"num_witness\": [" + std::to_string(A) + ", " + std::to_string(L) + ", " + std::to_string(S + L + 1) + "], \"num_challenge\": [1, 2, 1], \"evaluations\": " +
+           list(evals) + ", \"queries\": " + list(queries) + ", \"quotient\": {\"num_chunk\": " + std::to_string(dom.quotient_poly_degree) +
+           ", \"chunk_degree\": 1, \"numerator\": " + numerator + "}, \"transcript_initial_state\": " + fr(vk.transcript_repr) +
+           ", \"instance_committing_key\": null, \"linearization\": null, \"accumulator_indices\": []}";
+}
+
 // ------------------------------------------------------------------------------------------------ verify_proof (host only)
 struct VerifierParams {  // ParamsVerifierKZG: g2 and s_g2 (and G1's generator)
     pairing::G2Point g2, s_g2;
@@ -1088,7 +1360,8 @@ inline pairing::G1Point to_pairing_point(const XYZZ& p) {
 
 // plonk::verify_proof + VerifierSHPLONK + the final pairing (the "decide" of snark-verifier's KzgAs)
 inline bool verify_proof(const EvaluationDomain& dom, const VerifyingKey& vk, const VerifierParams& vp, const std::vector<Poly>& instances,
-                         const std::vector<uint8_t>& proof, std::string* why = nullptr) {
+                         const std::vector<uint8_t>& proof, std::string* why = nullptr,
+                         TranscriptKind transcript_kind = TranscriptKind::Blake2b) {
     auto fail = [&](const char* m) { if (why) *why = m; return false; };
     try {
         const ConstraintSystem& cs = vk.cs;
@@ -1096,7 +1369,7 @@ inline bool verify_proof(const EvaluationDomain& dom, const VerifyingKey& vk, co
         const uint32_t bf = cs.blinding_factors();
         const uint64_t u = n - bf - 1;
         const AuxLayout aux = aux_layout(cs);
-        Transcript tr(proof);
+        Transcript tr(proof, transcript_kind);
         tr.common_scalar(vk.transcript_repr);
         if (instances.size() != cs.num_instance) return fail("wrong number of instance columns");
         for (auto& inst : instances)

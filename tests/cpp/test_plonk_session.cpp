@@ -271,6 +271,40 @@ int main(int argc, char** argv) {
         ProofArtifacts po2 = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB201 + seed);
         REQUIRE(po2.proof != po.proof && verify_proof(dom, pk_o.vk, vp, C.instances, po2.proof, &why));
 
+        {   // ---- the reference's transcript: the same prover with snark-verifier's Poseidon transcript, and the protocol description a
+            // snark-verifier-style verifier needs (checked by tests/test_plonk_session.py with the model that accepts the reference's proofs)
+            ProofArtifacts pp = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB200 + seed, TranscriptKind::Poseidon);
+            REQUIRE(pp.proof.size() == po.proof.size() && pp.proof != po.proof);
+            REQUIRE(verify_proof(dom, pk_o.vk, vp, C.instances, pp.proof, &why, TranscriptKind::Poseidon));
+            REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, pp.proof, &why, TranscriptKind::Blake2b));  // the transcripts are not interchangeable
+            std::printf("poseidon_proof oracle %s\n", hex(pp.proof).c_str());
+            std::printf("protocol_json %s\n", export_protocol_json(dom, pk_o.vk).c_str());
+            const uint64_t u = n - C.cs.blinding_factors() - 1;
+            for (size_t c = 0; c < C.instances.size(); ++c) {
+                std::printf("instances %zu", c);
+                for (uint64_t r = 0; r < u; ++r) {
+                    uint8_t b[32];
+                    f_to_repr(C.instances[c][r], b);
+                    std::printf(" %s", hex(std::vector<uint8_t>(b, b + 32)).c_str());
+                }
+                std::printf("\n");
+            }
+            auto fq_hex = [&](const b200zk::Fq& v) {
+                uint8_t b[32];
+                serde::fq_to_le32(v, b);
+                return hex(std::vector<uint8_t>(b, b + 32));
+            };
+            std::printf("s_g2_le %s %s %s %s\n", fq_hex(vp.s_g2.x.c0).c_str(), fq_hex(vp.s_g2.x.c1).c_str(), fq_hex(vp.s_g2.y.c0).c_str(), fq_hex(vp.s_g2.y.c1).c_str());
+            if (mode == "both") {
+                ParamsKZG params2;
+                params2.k = k; params2.n = n; params2.g = g; params2.g_lagrange = gl;
+                DeviceOps dops2(params2, dom);
+                ProvingKey pk_d2 = keygen(dops2, dom, C.cs, C.fixed, *C.assembly);
+                ProofArtifacts pdp = create_proof(dops2, dom, pk_d2, C.advice, C.instances, 0xB200 + seed, TranscriptKind::Poseidon);
+                std::printf("poseidon_proof device %s\n", hex(pdp.proof).c_str());
+                REQUIRE(pdp.proof == pp.proof);
+            }
+        }
         if (mode == "both") {
             ParamsKZG params;
             ParamsKZG::setup(params, k, tau);  // on the device: g[i] = [tau^i]G, g_lagrange[i] = [L_i(tau)]G

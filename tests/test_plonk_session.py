@@ -46,6 +46,52 @@ def test_blake2b_transcript_hash_matches_hashlib():
         assert out == hashlib.blake2b(msg, digest_size=64, person=b"Halo2-Transcript").hexdigest()
 
 
+def parse_poseidon(out):
+    """the Poseidon-transcript proof, the exported protocol JSON, the instance values and [tau]G2 the driver printed"""
+    lines = out.splitlines()
+    proofs = {l.split()[1]: bytes.fromhex(l.split()[2]) for l in lines if l.startswith("poseidon_proof")}
+    proto_text = [l for l in lines if l.startswith("protocol_json")][0][len("protocol_json "):]
+    instances = [[int.from_bytes(bytes.fromhex(h), "little") for h in l.split()[2:]] for l in lines if l.startswith("instances")]
+    w = [int.from_bytes(bytes.fromhex(h), "little") for h in [l for l in lines if l.startswith("s_g2_le")][0].split()[1:]]
+    return proofs, proto_text, instances, ((w[0], w[1]), (w[2], w[3]))
+
+
+@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2)])
+def test_poseidon_transcript_proofs_are_accepted_by_the_snark_verifier_model(k, seed, variant, tmp_path):
+    """create_proof with snark-verifier's Poseidon transcript + export_protocol_json: the proof is accepted by
+    tests/snark_verifier_model.py -- the model that accepts the REFERENCE's shipped chunk and batch proofs
+    (tests/test_reference_proofs_kat.py) -- driven by nothing but the exported protocol; tampering is rejected; the exported
+    protocol is well-formed for the product's own reader (protocol_json.hpp)."""
+    from pairing_model import G2_GEN, g2_neg, pairing_check
+    from snark_verifier_model import PoseidonSpec, verify_plonk
+
+    _, out = run("oracle", k, seed, variant)
+    proofs, proto_text, instances, s_g2 = parse_poseidon(out)
+    proto, proof, spec = json.loads(proto_text), proofs["oracle"], PoseidonSpec()
+    decide = lambda lhs, rhs: pairing_check([(lhs, G2_GEN), (rhs, g2_neg(s_g2))])
+    lhs, rhs, info = verify_plonk(proto, instances, proof, spec)
+    assert decide(lhs, rhs)
+    assert proto["num_witness"] == ([3, 1, 4] if variant == 1 else [4, 2, 6]) and proto["num_challenge"] == [1, 2, 1]
+    for pos in (7, len(proof) // 2, len(proof) - 9):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        try:
+            l2, r2, _ = verify_plonk(proto, instances, bytes(bad), spec)
+        except ValueError:
+            continue
+        assert not decide(l2, r2), pos
+    if instances:
+        wrong = [instances[0][:]] + instances[1:]
+        wrong[0][0] ^= 1
+        l3, r3, _ = verify_plonk(proto, wrong, proof, spec)
+        assert not decide(l3, r3)
+    path = tmp_path / "ours.protocol"
+    path.write_text(proto_text)
+    import test_protocol_json as TP
+    rc, summary = TP.run(str(path))
+    assert rc == 0 and summary["k"] == k and summary["domain_matches_mirror"] is True and summary["proof_bytes_shplonk"] == len(proof)
+
+
 def key(k, seed, variant):
     return f"k{k}_seed{seed}" + ("" if variant == 1 else f"_v{variant}")
 
@@ -64,6 +110,8 @@ def test_session_on_the_device_gives_identical_proof_bytes(k, seed, variant):
     proofs, out = run("both", k, seed, variant)
     assert "device proof identical to the oracle's" in out
     assert proofs["device"] == proofs["oracle"]
+    pos_proofs, _, _, _ = parse_poseidon(out)
+    assert pos_proofs["device"] == pos_proofs["oracle"]  # and with snark-verifier's Poseidon transcript as well
     digests = json.load(open(DIGESTS))
     if key(k, seed, variant) in digests:
         assert hashlib.sha256(proofs["device"]).hexdigest() == digests[key(k, seed, variant)]
