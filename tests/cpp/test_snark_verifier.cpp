@@ -1,0 +1,75 @@
+// Driver for tests/test_snark_verifier_host.py: scroll-prover_b200/snark_verifier_b200.hpp on a case file
+//   {"protocol": <protocol JSON object>, "proof": "<hex>", "instances": [["<32-byte big-endian hex>", ...], ...],
+//    "s_g2": ["x_c1", "x_c0", "y_c1", "y_c0"]  (big-endian hex, EIP-197 word order; g2 is the generator)}
+// prints ACCEPT or REJECT <reason>.
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+#include "../../scroll-prover_b200/snark_verifier_b200.hpp"
+
+using namespace halo2_b200;
+
+static std::vector<uint8_t> unhex(const std::string& h) {
+    std::vector<uint8_t> out;
+    for (size_t i = 0; i + 1 < h.size(); i += 2) {
+        unsigned v;
+        std::sscanf(h.c_str() + i, "%2x", &v);
+        out.push_back((uint8_t)v);
+    }
+    return out;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    try {
+        std::ifstream f(argv[1], std::ios::binary);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        const std::string text = ss.str();
+        protocol::Json j = protocol::JsonParser(text).parse();
+        // re-serialising is not needed: the protocol object is parsed from its own span of the case file
+        size_t p0 = text.find("\"protocol\"");
+        p0 = text.find('{', p0);
+        int depth = 0;
+        size_t p1 = p0;
+        for (; p1 < text.size(); ++p1) {
+            if (text[p1] == '{') ++depth;
+            if (text[p1] == '}' && --depth == 0) break;
+        }
+        protocol::PlonkProtocol P = protocol::parse_protocol(text.substr(p0, p1 - p0 + 1));
+        std::vector<uint8_t> proof = unhex(j.at("proof").text);
+        std::vector<std::vector<Fr>> instances;
+        for (auto& col : j.at("instances").items) {
+            std::vector<Fr> c;
+            for (auto& w : col.items) {
+                std::vector<uint8_t> be = unhex(w.text), le(32);
+                for (int i = 0; i < 32; ++i) le[i] = be[31 - i];
+                Fr v;
+                if (!plonk::f_from_repr(le.data(), &v)) {
+                    std::printf("REJECT instance is not a field element\n");
+                    return 0;
+                }
+                c.push_back(v);
+            }
+            instances.push_back(c);
+        }
+        uint8_t g2w[128];
+        for (int i = 0; i < 4; ++i) {
+            std::vector<uint8_t> w = unhex(j.at("s_g2").items.at(i).text);
+            std::memcpy(g2w + 32 * i, w.data(), 32);
+        }
+        pairing::G2Point s_g2;
+        if (!pairing::g2_from_eip197(g2w, &s_g2) || !pairing::g2_on_curve(s_g2)) {
+            std::printf("REJECT malformed s_g2\n");
+            return 0;
+        }
+        std::string why;
+        bool ok = snark::verify(P, instances, proof, pairing::g2_generator(), s_g2, &why);
+        std::printf(ok ? "ACCEPT\n" : "REJECT %s\n", why.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        std::printf("REJECT exception: %s\n", e.what());
+        return 0;
+    }
+}

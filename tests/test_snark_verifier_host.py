@@ -1,0 +1,97 @@
+"""The product's host-side verifier for the reference's proof format (scroll-prover_b200/snark_verifier_b200.hpp: PlonkVerifier +
+PoseidonTranscript + Bdfg21 + KZG decider, C++ mirror of snark-verifier @ 948671c as scroll-prover's ChunkVerifier / BatchVerifier use
+it, /root/reference/integration/src/prove.rs:50-53,78-80):
+
+  * it ACCEPTS the reference's shipped chunk proofs (k = 25) and batch proofs (k = 26) from the protocol JSON, instances and proof
+    bytes alone -- the same decisions as the independent big-integer model (tests/snark_verifier_model.py);
+  * it rejects tampered proofs, wrong public inputs, a corrupted carried accumulator and another trusted setup;
+  * it ACCEPTS the proofs our own create_proof makes with the Poseidon transcript (plonk_b200.hpp) under the exported protocol --
+    i.e. prover and verifier of the product meet in the reference's format.
+CPU only.  The reference-proof cases are skipped where the reference tree is absent."""
+import base64
+import json
+import os
+import subprocess
+
+import pytest
+
+from pairing_model import Q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_snark_verifier.cpp")
+BIN = os.path.join(ROOT, "tests", "cpp", "test_snark_verifier")
+DATA = "/root/reference/integration/tests/test_data"
+have_ref = pytest.mark.skipif(not os.path.exists(os.path.join(DATA, "full_proof_1.json")), reason="reference tree not present")
+NEG_S_G2 = ((0x17944351223333f260ddc3b4af45191b856689eda9eab5cbcddbbe570ce860d2, 0x186282957db913abd99f91db59fe69922e95040603ef44c0bd7aa3adeef8f5ac),
+            (0x06ecdb9f9567f59ed2eee36e1e1d58797fd13cc97fafc2910f5e8a12f202fa9a, 0x06d971ff4a7467c3ec596ed6efc674572e32fd6f52b721f97e35b0b3d3546753))
+S_G2 = (NEG_S_G2[0], ((-NEG_S_G2[1][0]) % Q, (-NEG_S_G2[1][1]) % Q))
+
+
+def binary():
+    deps = [SRC] + [os.path.join(ROOT, "scroll-prover_b200", h) for h in ("snark_verifier_b200.hpp", "plonk_b200.hpp", "protocol_json.hpp", "pairing_bn254.hpp")]
+    if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
+        lib = os.path.join(ROOT, "scroll-prover_b200")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", BIN, SRC, "-L" + lib, "-lb200zk", "-Wl,-rpath," + lib])
+    return BIN
+
+
+def g2_words(q):
+    return ["%064x" % q[0][1], "%064x" % q[0][0], "%064x" % q[1][1], "%064x" % q[1][0]]
+
+
+def verdict(tmp_path, proto, proof: bytes, instances, s_g2=S_G2):
+    case = {"protocol": proto, "proof": proof.hex(), "instances": [["%064x" % v for v in col] for col in instances], "s_g2": g2_words(s_g2)}
+    path = tmp_path / "case.json"
+    path.write_text(json.dumps(case))
+    return subprocess.run([binary(), str(path)], capture_output=True, text=True, timeout=120).stdout.strip()
+
+
+def decode(entry):
+    raw = base64.b64decode(entry["instances"])
+    return json.loads(base64.b64decode(entry["protocol"])), base64.b64decode(entry["proof"]), [[int.from_bytes(raw[i:i + 32], "big") for i in range(0, len(raw), 32)]]
+
+
+@have_ref
+def test_reference_chunk_and_batch_proofs_are_accepted(tmp_path):
+    from test_reference_proofs_kat import chunk_entries
+
+    n = 0
+    for name, i, e in chunk_entries():
+        assert verdict(tmp_path, *decode(e)) == "ACCEPT", (name, i)
+        n += 1
+    for name in ("full_proof_batch_agg_1.json", "full_proof_batch_agg_2.json"):
+        assert verdict(tmp_path, *decode(json.load(open(os.path.join(DATA, name))))) == "ACCEPT", name
+        n += 1
+    assert n == 13
+
+
+@have_ref
+def test_tampering_is_rejected(tmp_path):
+    proto, proof, instances = decode(json.load(open(os.path.join(DATA, "full_proof_1.json")))["chunk_proofs"][0])
+    for pos in (3, 200, 300, 500, 850, 895):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert verdict(tmp_path, proto, bytes(bad), instances).startswith("REJECT"), pos
+    assert verdict(tmp_path, proto, proof[:-32], instances).startswith("REJECT")          # truncated
+    assert verdict(tmp_path, proto, proof + bytes(32), instances).startswith("REJECT")  # trailing bytes
+    wrong = [instances[0][:]]
+    wrong[0][20] ^= 1   # a public input
+    assert verdict(tmp_path, proto, proof, wrong).startswith("REJECT")
+    wrong = [instances[0][:]]
+    wrong[0][0] ^= 1    # a limb of the carried accumulator: the transcript changes AND the carried accumulator breaks
+    assert verdict(tmp_path, proto, proof, wrong).startswith("REJECT")
+    assert verdict(tmp_path, proto, proof, instances, s_g2=NEG_S_G2).startswith("REJECT")  # another (here: the negated) setup point
+    assert verdict(tmp_path, proto, proof, instances) == "ACCEPT"
+
+
+@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2)])
+def test_our_own_poseidon_proofs_are_accepted_under_the_exported_protocol(tmp_path, k, seed, variant):
+    import test_plonk_session as TS
+
+    _, out = TS.run("oracle", k, seed, variant)
+    proofs, proto_text, instances, s_g2 = TS.parse_poseidon(out)
+    proto, proof = json.loads(proto_text), proofs["oracle"]
+    assert verdict(tmp_path, proto, proof, instances, s_g2=s_g2) == "ACCEPT"
+    bad = bytearray(proof)
+    bad[len(bad) // 3] ^= 1
+    assert verdict(tmp_path, proto, bytes(bad), instances, s_g2=s_g2).startswith("REJECT")
