@@ -115,3 +115,13 @@ def test_session_on_the_device_gives_identical_proof_bytes(k, seed, variant):
     digests = json.load(open(DIGESTS))
     if key(k, seed, variant) in digests:
         assert hashlib.sha256(proofs["device"]).hexdigest() == digests[key(k, seed, variant)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,variant", [(14, 1), (16, 2)])
+def test_device_only_session_at_larger_sizes_is_accepted_by_both_verifiers(k, variant):
+    """2^14 / 2^16 rows (extended domain 2^16 / 2^18): SRS, keygen and create_proof entirely through the C ABI, Poseidon transcript;
+    the pairing-based verifiers (halo2-style and the snark-verifier mirror under the exported protocol) accept, a flipped byte is
+    rejected -- no oracle in the loop at this size."""
+    r = subprocess.run([binary(), "device", str(k), "3", str(variant)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK") and "accepted by both verifiers" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
