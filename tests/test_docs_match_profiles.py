@@ -63,7 +63,10 @@ def test_round2_numbers_quoted_in_design_and_readme():
     v2 = bench("bench_r02_v2.json")  # the final library of the round
     assert f"{v2['value']:.3f} s" in DESIGN and f"{v2['e2e']['value']:.3f} s" in DESIGN
     v3 = bench("bench_r02_v3.json")  # the final library, bounded in-line CPU sample
-    assert f"{v3['value']:.3f} s" in DESIGN and f"{v3['e2e']['value']:.3f} s" in DESIGN and f"{v3['value']:.2f} s" in README
+    assert f"{v3['value']:.3f} s" in DESIGN and f"{v3['e2e']['value']:.3f} s" in DESIGN
+    v4 = bench("bench_r02_v4.json")  # the last commit of the round
+    assert f"{v4['value']:.3f} s" in DESIGN and f"{v4['e2e']['value']:.3f} s" in DESIGN and f"{v4['value']:.2f} s" in README
+    assert v4["clocks"]["reasons"] == [] and v4["value"] <= v3["value"] * 1.01
     assert v3["cpu_baseline"]["scaled_layers"] == ["layer2"] and abs(v3["cpu_baseline"]["value"] / v2["cpu_baseline"]["value"] - 1) < 0.05
     assert v2["clocks"]["reasons"] == [] and v2["gpu_launches"] > 0 and 0.85 < v2["roofline"]["frac"] < 1.0
     ref = bench("bench_r02_reference_arm.json")
