@@ -16,9 +16,12 @@
 //                     directly, the <= 2 cut runs become partial records
 //   5 msm_combine_*   partial records: ordinary buckets by their head record, GIANT buckets (> 4L entries: millions
 //                     of equal digits in real witness columns) by a log-depth level reduction
-//   6 msm_rowcol_sums + msm_weighted_sums   sum_b b*B_b per bucket set with a short critical path
-//   7 msm_finish      Horner over bucket sets, normalisation to (x, y, 1)
+//   6 msm_rowcol_sums + msm_bit_sums   sum_b b*B_b per bucket set with a short critical path (row / column sums, then
+//                     bit-sliced weighted sums: independent subset sums instead of a dependent suffix scan)
+//   7 msm_finish      one block per column: Horner over the bit sums and the bucket sets, normalisation to (x, y, 1)
 // With a precomputed SRS (tables 2^(c*w) P_i, built at registration) all windows share ONE bucket set.
+// BATCHES: up to 32 columns over the same bases run through one pipeline (bucket set = column * Ws + window; the grids of
+// count / scatter carry the column in blockIdx.y), so the fixed phases are paid once per batch (msm_run_batch).
 // Zero scalars and zero digits are skipped (witness columns are mostly zeros / small values).
 #include "common.cuh"
 #include "ec.cuh"
