@@ -263,6 +263,7 @@ int32_t b200zk_msm_g1_batch(b200zk_ctx* ctx, const b200zk_srs* srs, const void* 
         if (n && !scalars[j]) return fail(ctx, B200ZK_E_INVALID, "msm_g1_batch: scalars[%u] is null", j);
     Guard g(ctx);
     if (!count) return B200ZK_OK;
+    try {
     const uint32_t pre_c = (srs->pre_c && n * 16 >= srs->n) ? srs->pre_c : 0;
     const uint32_t bmax = msm_max_batch(n, pre_c);
     B2_TRY(scratch_reserve(ctx, ctx->stage_out, sizeof(Jacobian) * count));
@@ -293,6 +294,9 @@ int32_t b200zk_msm_g1_batch(b200zk_ctx* ctx, const b200zk_srs* srs, const void* 
         if (host_bytes && (j0 + bmax < count || is_device_ptr(out_jacobian96))) B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return deliver(ctx, out_jacobian96, res, sizeof(Jacobian) * count);
+    } catch (const std::bad_alloc&) {  // nothing may unwind across the C boundary
+        return fail(ctx, B200ZK_E_OOM, "msm_g1_batch: host allocation failed");
+    }
 }
 
 int32_t b200zk_msm_g1_bases(b200zk_ctx* ctx, const void* g1_affine, const void* scalars, uint64_t n, void* out_jacobian96) {
@@ -432,10 +436,24 @@ static int32_t pipeline_init(b200zk_ctx* ctx) {
 // computes, and the commitments of a group's consecutive jobs over the same SRS go through ONE batched MSM pipeline
 // (msm_run_batch) -- for 2^20-row columns that is up to 16 columns per pipeline, a 2^24+ column is a group of its own.
 // No host synchronisation inside the loop.
+static int32_t run_column_jobs_impl(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k, const void* omega_inv32,
+                                    const void* extended_omega32, const void* extended_omega_inv32, uint32_t extended_k,
+                                    void* commits_out);
 int32_t b200zk_run_column_jobs(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k, const void* omega_inv32,
                                const void* extended_omega32, const void* extended_omega_inv32, uint32_t extended_k,
                                void* commits_out) {
     CHECK_CTX(ctx);
+    try {  // the job bookkeeping allocates host memory: nothing may unwind across the C boundary
+        return run_column_jobs_impl(ctx, jobs, count, k, omega_inv32, extended_omega32, extended_omega_inv32, extended_k, commits_out);
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, B200ZK_E_OOM, "run_column_jobs: host allocation failed");
+    } catch (...) {
+        return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: unexpected host-side failure");
+    }
+}
+static int32_t run_column_jobs_impl(b200zk_ctx* ctx, const b200zk_column_job* jobs, uint32_t count, uint32_t k, const void* omega_inv32,
+                                    const void* extended_omega32, const void* extended_omega_inv32, uint32_t extended_k,
+                                    void* commits_out) {
     if (k > 28 || (count && !jobs)) return fail(ctx, B200ZK_E_INVALID, "run_column_jobs: bad arguments");
     const uint64_t n = 1ull << k;
     bool any_commit = false, any_coeff = false, any_ext = false, any_quot = false;
@@ -637,7 +655,12 @@ int32_t b200zk_commit_columns(b200zk_ctx* ctx, const b200zk_srs* srs, const void
     CHECK_CTX(ctx);
     if (mode < 0 || mode > 3) return fail(ctx, B200ZK_E_INVALID, "commit_columns: mode must be 0 (commit), 1 (+coeff), 2 (+coeff+extended), 3 (coeff+extended only)");
     if (count && !host_cols) return fail(ctx, B200ZK_E_INVALID, "commit_columns: null host_cols");
-    std::vector<b200zk_column_job> jobs(count);
+    std::vector<b200zk_column_job> jobs;
+    try {
+        jobs.resize(count);
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, B200ZK_E_OOM, "commit_columns: host allocation failed");
+    }
     for (uint32_t j = 0; j < count; ++j) {
         jobs[j].host_values = host_cols[j];
         jobs[j].srs = srs;
