@@ -1,7 +1,9 @@
 """The reference's EVM verifier PROGRAM run on the reference's shipped proof (SURVEY.md §8(c) fixture 3, §8(f).4; the `verifier
 bytecode check` of BASELINE configs[4]): release-v0.13.1/evm_verifier.yul (the Yul source of evm_verifier.bin) is interpreted
 statement by statement (tests/yul_verifier.py) on calldata = proof.data with pi.data spliced in after the 12 accumulator limbs (the layer-6 EVM proof).  It must accept,
-and must reject when a byte of the proof or of the public input is flipped.
+and must reject when a byte of the proof or of the public input is flipped.  The deployed artefact itself, evm_verifier.bin, is
+run too: a small stack machine (tests/evm_bytecode.py) executes its constructor, takes the 13 987-byte runtime it returns and
+calls it with the same calldata -- same verdicts, same precompile and Keccak call counts as the Yul source.
 
 The elliptic-curve precompiles (ecAdd 0x06, ecMul 0x07, ecPairing 0x08) are served twice: by the independent big-integer model
 and by the PRODUCT's host-side code (csrc/ec.cuh group law + pairing_bn254.hpp, through tests/host_emul/libpairing_host.so) --
@@ -123,3 +125,39 @@ def test_reference_verifier_program_on_the_products_host_curve_and_pairing_code(
         bad[pos] ^= 1
         ok2, _ = verify(yul, bytes(bad), add, mul, pairing)
         assert not ok2, pos
+
+
+# ---- the deployed bytecode itself (evm_verifier.bin), not only its Yul source
+def load_bin():
+    return open(os.path.join(REL, "evm_verifier.bin"), "rb").read()
+
+
+def test_reference_verifier_bytecode_deploys_and_accepts_the_shipped_proof():
+    from evm_bytecode import call, deploy
+
+    _, calldata = load()
+    runtime = deploy(load_bin())
+    assert len(runtime) == 0x36A3  # the size the constructor pushes before CODECOPY
+    ok, m = call(runtime, calldata, m_add, m_mul, m_pairing)
+    assert ok
+    # same work as the Yul source does: one pairing, the same EC and hash call counts
+    _, y = verify(load()[0], calldata, m_add, m_mul, m_pairing)
+    assert m.precompile_calls == y.precompile_calls and m.keccak_calls == y.keccak_calls
+
+
+def test_reference_verifier_bytecode_on_the_products_host_curve_and_pairing_code():
+    from evm_bytecode import call, deploy
+
+    _, calldata = load()
+    runtime = deploy(load_bin())
+    add, mul, pairing = h_add_mul(host_lib())
+    ok, m = call(runtime, calldata, add, mul, pairing)
+    assert ok and m.precompile_calls[8] == 1
+    for pos in (40, 384 + 5, 800 + 5, 800 + 700, len(calldata) - 3):
+        bad = bytearray(calldata)
+        bad[pos] ^= 1
+        ok2, _ = call(runtime, bytes(bad), add, mul, pairing)
+        assert not ok2, pos
+    # a truncated proof is rejected as well (CALLDATALOAD past the end reads zeros: not a curve point / wrong pairing)
+    ok3, _ = call(runtime, calldata[:-32], add, mul, pairing)
+    assert not ok3
