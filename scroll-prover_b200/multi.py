@@ -1,10 +1,13 @@
-"""Multi-GPU host logic: one process per GPU (torch.distributed, NCCL on the GPU box / gloo in CPU tests).
+"""Host-side planning helpers for the one-process-per-GPU launch, and the CPU twin of the sharded MSM.
 
-Two strategies, both without a data-path collective on field data:
-  * job fan-out  — independent columns / commits of one proof are distributed over ranks (assign_jobs);
-  * point-range MSM sharding — rank r holds bases[lo_r:hi_r] resident and receives the matching scalar slice;
-    each rank computes a full local Pippenger, the 96-byte partial points are all-gathered (NCCL has no G1
-    reduction) and every rank adds them with b200zk_g1_sum.
+The PRODUCT's multi-GPU data path lives inside the C ABI (csrc/comm.cu: the context-owned NCCL communicator,
+b200zk_msm_g1_sharded, b200zk_graph_evaluate_rows + b200zk_allgather_rows; Python: Context.comm_init, Srs.msm_sharded).  This module
+holds what needs no device:
+  * shard_range  — the contiguous point / row range of a rank; b200zk_shard_range must return the same partition
+                   (tests/test_multi_rank.py holds the two together);
+  * assign_jobs  — longest-processing-time placement of a proof layer's independent column jobs over ranks;
+  * msm_sharded  — the same gather-and-sum flow as b200zk_msm_g1_sharded over ANY torch.distributed backend, with the local MSM
+                   and the final sum passed in: the world-2 gloo tests run it on CPU with the oracle standing in for the device.
 """
 from __future__ import annotations
 
