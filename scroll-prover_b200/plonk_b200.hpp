@@ -374,15 +374,16 @@ class Transcript {
 struct Expr;
 using ExprP = std::shared_ptr<const Expr>;
 struct Expr {
-    enum Kind { Constant, Fixed, Advice, Instance, Negated, Sum, Product, Scaled } kind;
+    enum Kind { Constant, Fixed, Advice, Instance, Negated, Sum, Product, Scaled, Challenge } kind;
     Fr c{};          // Constant, Scaled
-    uint32_t col = 0;  // column index
+    uint32_t col = 0;  // column index (Challenge: index of the challenge)
     int32_t rot = 0;   // Rotation
     ExprP a, b;
     static ExprP constant(const Fr& v) { auto e = std::make_shared<Expr>(); e->kind = Constant; e->c = v; return e; }
     static ExprP fixed(uint32_t col, int32_t rot = 0) { auto e = std::make_shared<Expr>(); e->kind = Fixed; e->col = col; e->rot = rot; return e; }
     static ExprP advice(uint32_t col, int32_t rot = 0) { auto e = std::make_shared<Expr>(); e->kind = Advice; e->col = col; e->rot = rot; return e; }
     static ExprP instance(uint32_t col, int32_t rot = 0) { auto e = std::make_shared<Expr>(); e->kind = Instance; e->col = col; e->rot = rot; return e; }
+    static ExprP challenge(uint32_t index) { auto e = std::make_shared<Expr>(); e->kind = Challenge; e->col = index; return e; }  // Expression::Challenge
     static ExprP neg(ExprP x) { auto e = std::make_shared<Expr>(); e->kind = Negated; e->a = x; return e; }
     static ExprP sum(ExprP x, ExprP y) { auto e = std::make_shared<Expr>(); e->kind = Sum; e->a = x; e->b = y; return e; }
     static ExprP sub(ExprP x, ExprP y) { return sum(x, neg(y)); }
@@ -391,7 +392,7 @@ struct Expr {
 
     uint32_t degree() const {
         switch (kind) {
-            case Constant: return 0;
+            case Constant: case Challenge: return 0;
             case Fixed: case Advice: case Instance: return 1;
             case Negated: case Scaled: return a->degree();
             case Sum: return std::max(a->degree(), b->degree());
@@ -406,6 +407,7 @@ struct Expr {
         switch (kind) {
             case Constant: return constant(c);
             case Fixed: case Advice: case Instance: return query((int)kind, col, rot);
+            case Challenge: return query((int)kind, col, 0);  // the leaf closure resolves challenges by index
             case Negated: return negated(a->evaluate<T>(constant, query, negated, sum, product, scaled));
             case Sum: return sum(a->evaluate<T>(constant, query, negated, sum, product, scaled), b->evaluate<T>(constant, query, negated, sum, product, scaled));
             case Product: return product(a->evaluate<T>(constant, query, negated, sum, product, scaled), b->evaluate<T>(constant, query, negated, sum, product, scaled));
@@ -435,6 +437,7 @@ inline ValueSource add_expression(GraphEvaluator& ev, const Expr& e) {
         case Expr::Fixed: return ValueSource::Fixed(e.col, ev.add_rotation(e.rot));
         case Expr::Advice: return ValueSource::Advice(e.col, ev.add_rotation(e.rot));
         case Expr::Instance: return ValueSource::Instance(e.col, ev.add_rotation(e.rot));
+        case Expr::Challenge: return ValueSource::Challenge(e.col);
         case Expr::Negated: return ev.add(B200ZK_CALC_NEGATE, add_expression(ev, *e.a));
         case Expr::Sum: {
             if (e.b->kind == Expr::Negated) return ev.add(B200ZK_CALC_SUB, add_expression(ev, *e.a), add_expression(ev, *e.b->a));  // a + (-b) = a - b, as upstream
@@ -460,6 +463,17 @@ struct ConstraintSystem {
     std::vector<ExprP> gates;             // every polynomial identity (selector already multiplied in), in gate order
     std::vector<Lookup> lookups;
     std::vector<Column> permutation;      // columns under equality constraints, in enable_equality order
+    // multi-phase proving (ConstraintSystem::advice_column_phase / challenge_phase): advice column c is assigned in phase
+    // advice_phase[c] (empty = every column in the first phase); challenge i becomes available after the commitments of phase
+    // challenge_phase[i] and may be used by the witness of later phases and by any expression (Expr::challenge(i))
+    std::vector<uint8_t> advice_phase, challenge_phase;
+    uint32_t phase_of_advice(uint32_t col) const { return advice_phase.empty() ? 0 : advice_phase[col]; }
+    uint32_t num_phases() const {
+        uint32_t p = 0;
+        for (auto v : advice_phase) p = std::max<uint32_t>(p, v);
+        for (auto v : challenge_phase) p = std::max<uint32_t>(p, v);
+        return p + 1;
+    }
     std::vector<std::pair<uint32_t, int32_t>> fixed_queries, advice_queries, instance_queries;  // in first-use order
 
     void finalize() {  // collects the queries the way ConstraintSystem::query_*_index registers them
@@ -670,6 +684,12 @@ inline Fr vk_transcript_repr(const VerifyingKey& vk) {
     u32((uint32_t)vk.cs.lookups.size()); u32((uint32_t)vk.cs.permutation.size()); u32(vk.cs.degree());
     for (auto& q : vk.cs.advice_queries) { u32(q.first); u32((uint32_t)q.second); }
     for (auto& q : vk.cs.fixed_queries) { u32(q.first); u32((uint32_t)q.second); }
+    if (!vk.cs.advice_phase.empty() || !vk.cs.challenge_phase.empty()) {  // single-phase keys hash as before
+        u32((uint32_t)vk.cs.advice_phase.size());
+        for (auto v : vk.cs.advice_phase) u32(v);
+        u32((uint32_t)vk.cs.challenge_phase.size());
+        for (auto v : vk.cs.challenge_phase) u32(v);
+    }
     uint8_t c[32];
     for (auto& p : vk.fixed_commitments) { serde::g1_to_compressed(p, c); h.update(c, 32); }
     for (auto& p : vk.permutation_commitments) { serde::g1_to_compressed(p, c); h.update(c, 32); }
@@ -900,9 +920,15 @@ struct ProofArtifacts {  // what a caller may want beside the bytes (tests)
     size_t n_commitments = 0, n_evals = 0;
 };
 
-// plonk::create_proof for one circuit instance with one phase.  advice: Lagrange values of every advice column (usable rows
-// filled by the caller's synthesis; the blinding rows are overwritten here), instances: Lagrange values of the instance columns.
-inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const ProvingKey& pk, std::vector<Poly> advice,
+// The caller's witness generation (upstream: Circuit::synthesize run once per phase through WitnessCollection): called for
+// phase 0, 1, ... with the challenges squeezed so far (entries of later phases are zero) and the advice table; it fills the usable
+// rows of the columns of THAT phase (columns of earlier phases hold what was committed, writes to them are discarded).
+using WitnessFn = std::function<void(uint32_t phase, const std::vector<Fr>& challenges, std::vector<Poly>& advice)>;
+
+// plonk::create_proof for one circuit instance.  Per phase: witness, blinding rows, commit_lagrange of that phase's advice columns,
+// then the phase's challenges from the transcript (prover.rs `for current_phase in pk.vk.cs.phases()`); instances: Lagrange values
+// of the instance columns.
+inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const ProvingKey& pk, const WitnessFn& synthesize,
                                    const std::vector<Poly>& instances, uint64_t rng_seed,
                                    TranscriptKind transcript_kind = TranscriptKind::Blake2b) {
     const ConstraintSystem& cs = pk.vk.cs;
@@ -910,7 +936,8 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     const uint32_t bf = cs.blinding_factors();
     const uint64_t u = n - bf - 1;  // last usable row index (the l_last row); rows > u are blinding rows
     const AuxLayout aux = aux_layout(cs);
-    if (advice.size() != cs.num_advice || instances.size() != cs.num_instance) throw Panic("create_proof: wrong number of columns");
+    if (instances.size() != cs.num_instance) throw Panic("create_proof: wrong number of columns");
+    if (!cs.advice_phase.empty() && cs.advice_phase.size() != cs.num_advice) throw Panic("create_proof: one phase per advice column");
     Rng rng(rng_seed);
     Transcript tr(transcript_kind);
     ProofArtifacts art;
@@ -929,13 +956,25 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     for (auto& inst : instances)
         for (uint64_t r = 0; r < u; ++r) tr.common_scalar(inst[r]);
 
-    // 1. advice: blinding rows, commitments (commit_lagrange), coefficient form, extended cosets
-    std::vector<Poly> advice_polys, advice_cosets;
-    for (auto& col : advice) {
-        if (col.size() != n) throw Panic("create_proof: advice column length");
-        for (uint64_t r = u; r < n; ++r) col[r] = rng.fr();  // unusable_rows_start = n - (blinding_factors + 1)
+    // 1. advice, phase by phase: witness, blinding rows, commitments (commit_lagrange), the phase's challenges; then the
+    //    coefficient form and the extended cosets of every column
+    std::vector<Poly> advice(cs.num_advice, Poly(n, f_zero())), advice_polys, advice_cosets;
+    std::vector<Fr> challenges(cs.challenge_phase.size(), f_zero());
+    for (uint32_t phase = 0; phase < cs.num_phases(); ++phase) {
+        std::vector<Poly> work = advice;
+        synthesize(phase, challenges, work);
+        if (work.size() != cs.num_advice) throw Panic("create_proof: wrong number of columns");
+        for (uint32_t c = 0; c < cs.num_advice; ++c) {
+            if (cs.phase_of_advice(c) != phase) continue;
+            if (work[c].size() != n) throw Panic("create_proof: advice column length");
+            advice[c] = std::move(work[c]);
+            for (uint64_t r = u; r < n; ++r) advice[c][r] = rng.fr();  // unusable_rows_start = n - (blinding_factors + 1)
+        }
+        for (uint32_t c = 0; c < cs.num_advice; ++c)
+            if (cs.phase_of_advice(c) == phase) write_point(ops.commit_lagrange(advice[c]));
+        for (size_t i = 0; i < challenges.size(); ++i)
+            if (cs.challenge_phase[i] == phase) challenges[i] = tr.squeeze_challenge();
     }
-    for (auto& col : advice) write_point(ops.commit_lagrange(col));
     for (auto& col : advice) {
         advice_polys.push_back(ops.lagrange_to_coeff(col));
         advice_cosets.push_back(ops.coeff_to_extended(advice_polys.back()));
@@ -946,6 +985,7 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     auto lagrange_query = [&](uint64_t row) {
         return [&, row](int kind, uint32_t col, int32_t rot) -> Fr {
             uint64_t r = (uint64_t)(((int64_t)row + rot) % (int64_t)n + (int64_t)n) % n;
+            if (kind == Expr::Challenge) return challenges[col];
             if (kind == Expr::Fixed) return pk.fixed_values[col][r];
             if (kind == Expr::Advice) return advice[col][r];
             return instances[col][r];
@@ -1045,10 +1085,9 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     }
     for (auto& c : lk_cosets) advice_tab.push_back(&c);
     for (auto& c : instance_cosets) instance_tab.push_back(&c);
-    const std::vector<Fr> no_challenges;
-    if (!pk.gates.calcs.empty()) ops.graph_evaluate(pk.gates, fixed_tab, advice_tab, instance_tab, no_challenges, beta, gamma, theta, y, h_ext);
-    if (!cs.permutation.empty()) ops.graph_evaluate(pk.permutation, fixed_tab, advice_tab, instance_tab, no_challenges, beta, gamma, theta, y, h_ext);
-    for (auto& prog : pk.lookups) ops.graph_evaluate(prog, fixed_tab, advice_tab, instance_tab, no_challenges, beta, gamma, theta, y, h_ext);
+    if (!pk.gates.calcs.empty()) ops.graph_evaluate(pk.gates, fixed_tab, advice_tab, instance_tab, challenges, beta, gamma, theta, y, h_ext);
+    if (!cs.permutation.empty()) ops.graph_evaluate(pk.permutation, fixed_tab, advice_tab, instance_tab, challenges, beta, gamma, theta, y, h_ext);
+    for (auto& prog : pk.lookups) ops.graph_evaluate(prog, fixed_tab, advice_tab, instance_tab, challenges, beta, gamma, theta, y, h_ext);
     {   // EvaluationDomain::divide_by_vanishing_poly: (zeta * w_ext^i)^n - 1 takes 2^(extended_k - k) distinct values
         const size_t period = (size_t)1 << (dom.extended_k - dom.k);
         std::vector<Fr> t_inv(period);
@@ -1197,6 +1236,19 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
     return art;
 }
 
+// the witness known up front (single-phase circuits, or a caller that already holds every phase's columns)
+inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const ProvingKey& pk, std::vector<Poly> advice,
+                                   const std::vector<Poly>& instances, uint64_t rng_seed,
+                                   TranscriptKind transcript_kind = TranscriptKind::Blake2b) {
+    if (advice.size() != pk.vk.cs.num_advice) throw Panic("create_proof: wrong number of columns");
+    const ConstraintSystem& cs = pk.vk.cs;
+    WitnessFn fill = [&](uint32_t phase, const std::vector<Fr>&, std::vector<Poly>& table) {
+        for (uint32_t c = 0; c < cs.num_advice; ++c)
+            if (cs.phase_of_advice(c) == phase) table[c] = advice[c];
+    };
+    return create_proof(ops, dom, pk, fill, instances, rng_seed, transcript_kind);
+}
+
 // ------------------------------------------------------------------------------------------------ snark-verifier protocol export
 // What snark-verifier's `compile(params, vk, config)` (system/halo2.rs) produces for a halo2 verifying key, written for OUR key in the
 // serde_json schema of the reference's `*.protocol` files (protocol_json.hpp reads it back): polynomial indices = preprocessed (fixed,
@@ -1213,6 +1265,21 @@ inline std::string export_protocol_json(const EvaluationDomain& dom, const Verif
     const size_t n_pre = vk.fixed_commitments.size() + vk.permutation_commitments.size(), n_inst = cs.num_instance;
     const size_t A = cs.num_advice, L = cs.lookups.size(), S = aux.n_sets;
     const size_t w0 = n_pre + n_inst, p_m = w0 + A, p_z = p_m + L, p_phi = p_z + S, p_random = p_phi + L, p_quotient = p_random + 1;
+    // snark-verifier orders witnesses and challenges by phase (Polynomials::new `remapping`): the index of advice column c among
+    // the witnesses is its position in phase-major order -- which is the order create_proof commits them in
+    const uint32_t P = cs.num_phases();
+    std::vector<size_t> advice_index(A), challenge_index(cs.challenge_phase.size()), advice_per_phase(P, 0), challenge_per_phase(P, 0);
+    {
+        size_t next = 0;
+        for (uint32_t ph = 0; ph < P; ++ph)
+            for (uint32_t c = 0; c < A; ++c)
+                if (cs.phase_of_advice(c) == ph) { advice_index[c] = next++; advice_per_phase[ph]++; }
+        next = 0;
+        for (uint32_t ph = 0; ph < P; ++ph)
+            for (size_t i = 0; i < challenge_index.size(); ++i)
+                if (cs.challenge_phase[i] == ph) { challenge_index[i] = next++; challenge_per_phase[ph]++; }
+    }
+    const int C = (int)challenge_index.size();  // theta, beta, gamma, y follow the circuit's own challenges
     auto limbs = [](const uint64_t l[4]) {
         return "[" + std::to_string(l[0]) + ", " + std::to_string(l[1]) + ", " + std::to_string(l[2]) + ", " + std::to_string(l[3]) + "]";
     };
@@ -1231,20 +1298,21 @@ inline std::string export_protocol_json(const EvaluationDomain& dom, const Verif
     auto sum = [](const std::string& a, const std::string& b) { return "{\"Sum\": [" + a + ", " + b + "]}"; };
     auto sub = [&](const std::string& a, const std::string& b) { return sum(a, neg(b)); };
     auto mul = [](const std::string& a, const std::string& b) { return "{\"Product\": [" + a + ", " + b + "]}"; };
-    const std::string theta = challenge(0), beta = challenge(1), gamma = challenge(2), one = constant(f_one());
+    const std::string theta = challenge(C), beta = challenge(C + 1), gamma = challenge(C + 2), one = constant(f_one());
     std::function<std::string(const Expr&)> expr = [&](const Expr& e) -> std::string {
         switch (e.kind) {
             case Expr::Constant: return constant(e.c);
             case Expr::Fixed: return poly(e.col, e.rot);
-            case Expr::Advice: return poly(w0 + e.col, e.rot);
+            case Expr::Advice: return poly(w0 + advice_index[e.col], e.rot);
             case Expr::Instance: return poly(n_pre + e.col, e.rot);
+            case Expr::Challenge: return challenge((int)challenge_index[e.col]);
             case Expr::Negated: return neg(expr(*e.a));
             case Expr::Sum: return sum(expr(*e.a), expr(*e.b));
             case Expr::Product: return mul(expr(*e.a), expr(*e.b));
             default: return "{\"Scaled\": [" + expr(*e.a) + ", " + fr(e.c) + "]}";
         }
     };
-    auto column = [&](const Column& c) { return c.kind == Expr::Advice ? poly(w0 + c.index, 0) : (c.kind == Expr::Fixed ? poly(c.index, 0) : poly(n_pre + c.index, 0)); };
+    auto column = [&](const Column& c) { return c.kind == Expr::Advice ? poly(w0 + advice_index[c.index], 0) : (c.kind == Expr::Fixed ? poly(c.index, 0) : poly(n_pre + c.index, 0)); };
     const int32_t last = -(int32_t)(bf + 1);
     std::string l_blind = lagrange(-1);
     for (uint32_t i = 2; i <= bf; ++i) l_blind = sum(l_blind, lagrange(-(int64_t)i));
@@ -1283,11 +1351,11 @@ inline std::string export_protocol_json(const EvaluationDomain& dom, const Verif
     }
     // evaluations (write order of create_proof) and queries (order of its SHPLONK opening claims)
     std::vector<std::pair<size_t, int32_t>> evals, queries, q_fixed, q_sigma;
-    for (auto& q : cs.advice_queries) evals.push_back({w0 + q.first, q.second});
+    for (auto& q : cs.advice_queries) evals.push_back({w0 + advice_index[q.first], q.second});
     for (auto& q : cs.fixed_queries) { evals.push_back({q.first, q.second}); q_fixed.push_back({q.first, q.second}); }
     evals.push_back({p_random, 0});
     for (size_t i = 0; i < vk.permutation_commitments.size(); ++i) { evals.push_back({vk.fixed_commitments.size() + i, 0}); q_sigma.push_back({vk.fixed_commitments.size() + i, 0}); }
-    for (auto& q : cs.advice_queries) queries.push_back({w0 + q.first, q.second});
+    for (auto& q : cs.advice_queries) queries.push_back({w0 + advice_index[q.first], q.second});
     for (size_t sidx = 0; sidx < S; ++sidx)
         for (int32_t rot : {0, 1, last}) {
             if (rot == last && sidx + 1 == S) continue;
@@ -1310,18 +1378,25 @@ inline std::string export_protocol_json(const EvaluationDomain& dom, const Verif
     };
     std::string numerator = "{\"DistributePowers\": [[";
     for (size_t i = 0; i < terms.size(); ++i) numerator += (i ? ", " : "") + terms[i];
-    numerator += "], " + challenge(3) + "]}";
+    numerator += "], " + challenge(C + 3) + "]}";
     std::string pre = "[";
     size_t cnt = 0;
     for (auto* v : {&vk.fixed_commitments, &vk.permutation_commitments})
         for (auto& pt : *v) pre += std::string(cnt++ ? ", " : "") + "{\"x\": " + fq(pt.x) + ", \"y\": " + fq(pt.y) + "}";
     pre += "]";
+    std::string num_witness, num_challenge;  // per phase, then [lookup m] [z, phi, random]; theta joins the last phase's challenges
+    for (uint32_t ph = 0; ph < P; ++ph) {
+        num_witness += std::to_string(advice_per_phase[ph]) + ", ";
+        num_challenge += std::to_string(challenge_per_phase[ph] + (ph + 1 == P ? 1 : 0)) + ", ";
+    }
+    num_witness += std::to_string(L) + ", " + std::to_string(S + L + 1);
+    num_challenge += "2, 1";
     std::string inst = "[";
     for (size_t i = 0; i < n_inst; ++i) inst += std::string(i ? ", " : "") + std::to_string(u);
     inst += "]";
     return "{\"domain\": {\"k\": " + std::to_string(dom.k) + ", \"n\": " + std::to_string(dom.n) + ", \"n_inv\": " + fr(dom.ifft_divisor) + ", \"gen\": " +
            fr(dom.omega) + ", \"gen_inv\": " + fr(dom.omega_inv) + "}, \"preprocessed\": " + pre + ", \"num_instance\": " + inst +
-           ", \"num_witness\": [" + std::to_string(A) + ", " + std::to_string(L) + ", " + std::to_string(S + L + 1) + "], \"num_challenge\": [1, 2, 1], \"evaluations\": " +
+           ", \"num_witness\": [" + num_witness + "], \"num_challenge\": [" + num_challenge + "], \"evaluations\": " +
            list(evals) + ", \"queries\": " + list(queries) + ", \"quotient\": {\"num_chunk\": " + std::to_string(dom.quotient_poly_degree) +
            ", \"chunk_degree\": 1, \"numerator\": " + numerator + "}, \"transcript_initial_state\": " + fr(vk.transcript_repr) +
            ", \"instance_committing_key\": null, \"linearization\": null, \"accumulator_indices\": []}";
@@ -1374,8 +1449,14 @@ inline bool verify_proof(const EvaluationDomain& dom, const VerifyingKey& vk, co
         if (instances.size() != cs.num_instance) return fail("wrong number of instance columns");
         for (auto& inst : instances)
             for (uint64_t r = 0; r < u; ++r) tr.common_scalar(inst[r]);
-        std::vector<serde::G1Point> advice_c, m_c, z_c, phi_c, h_c;
-        for (uint32_t i = 0; i < cs.num_advice; ++i) advice_c.push_back(tr.read_point());
+        std::vector<serde::G1Point> advice_c(cs.num_advice), m_c, z_c, phi_c, h_c;
+        std::vector<Fr> challenges(cs.challenge_phase.size(), f_zero());
+        for (uint32_t phase = 0; phase < cs.num_phases(); ++phase) {  // per phase: its advice commitments, then its challenges
+            for (uint32_t c = 0; c < cs.num_advice; ++c)
+                if (cs.phase_of_advice(c) == phase) advice_c[c] = tr.read_point();
+            for (size_t i = 0; i < challenges.size(); ++i)
+                if (cs.challenge_phase[i] == phase) challenges[i] = tr.squeeze_challenge();
+        }
         const Fr theta = tr.squeeze_challenge();
         for (size_t i = 0; i < cs.lookups.size(); ++i) m_c.push_back(tr.read_point());
         const Fr beta = tr.squeeze_challenge(), gamma = tr.squeeze_challenge();
@@ -1419,6 +1500,7 @@ inline bool verify_proof(const EvaluationDomain& dom, const VerifyingKey& vk, co
             return acc;
         };
         auto query = [&](int kind, uint32_t col, int32_t rot) -> Fr {
+            if (kind == Expr::Challenge) return challenges[col];
             if (kind == Expr::Instance) return instance_eval(col, rot);
             auto& qs = kind == Expr::Fixed ? cs.fixed_queries : cs.advice_queries;
             auto& ev = kind == Expr::Fixed ? fixed_e : advice_e;

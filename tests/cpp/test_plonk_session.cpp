@@ -30,6 +30,7 @@ struct Circuit {
     std::vector<Poly> fixed;
     std::unique_ptr<Assembly> assembly;
     std::vector<Poly> advice, instances;
+    WitnessFn synth;  // multi-phase circuits: the witness per phase, from the challenges (advice stays empty)
 };
 
 // fixed: 0 q_mul, 1 q_add, 2 q_lookup, 3 table, 4 q_pub, 5 q_rot, 6 constants        advice: 0 a, 1 b, 2 c        instance: 0
@@ -173,6 +174,89 @@ static Circuit build_wide(uint32_t k, uint64_t seed, int sabotage) {
     return C;
 }
 
+// Variant 3 ("phased"): TWO phases with a challenge each, the way the zkEVM circuits use them (random linear combinations):
+//   advice 0 a, 1 b in phase 0;  2 acc, 3 d in phase 1;  challenge 0 `r` after phase 0, challenge 1 `s` after phase 1
+//   fixed: 0 q_first, 1 q_rlc, 2 q_mul, 3 q_pair, 4 q_lookup, 5 t0, 6 t1
+//   acc[0] = a[0], acc[i+1] = acc[i] r + a[i+1] (the witness of phase 1 NEEDS r);  d = a b + r on the q_mul rows;
+//   q_pair rows: (a(wX) - b) + s (b(wX) - a) = 0 -- two constraints folded with the LAST phase's challenge;
+//   lookup: q_lookup (a + r b) in t0 + r t1 -- input and table combined with a challenge instead of theta;
+//   copies: a[2] = d[9] (a phase-0 cell into a phase-1 cell), acc[4] = d[11].
+static Circuit build_phased(uint32_t k, uint64_t seed, int sabotage) {
+    Circuit C;
+    const uint64_t n = 1ull << k;
+    ConstraintSystem& cs = C.cs;
+    cs.num_fixed = 7;
+    cs.num_advice = 4;
+    cs.num_instance = 0;
+    cs.advice_phase = {0, 0, 1, 1};
+    cs.challenge_phase = {0, 1};
+    auto a = Expr::advice(0), b = Expr::advice(1), acc = Expr::advice(2), d = Expr::advice(3);
+    auto r = Expr::challenge(0), sc = Expr::challenge(1);
+    cs.gates.push_back(Expr::mul(Expr::fixed(0), Expr::sub(acc, a)));                                                          // q_first (acc - a)
+    cs.gates.push_back(Expr::mul(Expr::fixed(1), Expr::sub(Expr::advice(2, 1), Expr::sum(Expr::mul(acc, r), Expr::advice(0, 1)))));  // q_rlc
+    cs.gates.push_back(Expr::mul(Expr::fixed(2), Expr::sub(d, Expr::sum(Expr::mul(a, b), r))));                                // q_mul (d - a b - r)
+    cs.gates.push_back(Expr::mul(Expr::fixed(3), Expr::sum(Expr::sub(Expr::advice(0, 1), b), Expr::mul(sc, Expr::sub(Expr::advice(1, 1), a)))));  // q_pair
+    Lookup lk;
+    lk.inputs = {Expr::mul(Expr::fixed(4), Expr::sum(a, Expr::mul(r, b)))};
+    lk.table = {Expr::sum(Expr::fixed(5), Expr::mul(r, Expr::fixed(6)))};
+    cs.lookups.push_back(lk);
+    cs.permutation = {{Expr::Advice, 0}, {Expr::Advice, 3}, {Expr::Advice, 2}};
+    cs.finalize();
+    const uint32_t bf = cs.blinding_factors();
+    const uint64_t u = n - bf - 1, T = std::min<uint64_t>(u - 1, 40);
+    C.fixed.assign(7, Poly(n, f_zero()));
+    C.assembly.reset(new Assembly(3, n));
+    for (uint64_t j = 1; j <= T; ++j) { C.fixed[5][j] = f_u64(j); C.fixed[6][j] = f_u64(j * j + 1); }  // row 0 is (0, 0): the disabled rows
+    C.fixed[0][0] = f_one();
+    std::vector<int> forced(n, 0), lookup_row(n, 0);
+    for (uint64_t row = 0; row < u; ++row) {
+        if (row + 1 < u) C.fixed[1][row] = f_one();
+        if (row % 2 == 0) C.fixed[2][row] = f_one();
+        if (row % 7 == 3 && row + 1 < u) { C.fixed[3][row] = f_one(); forced[row + 1] = 1; }
+    }
+    for (uint64_t row = 0; row < u; ++row)
+        if (row % 4 == 1 && !forced[row] && row != 2) { C.fixed[4][row] = f_one(); lookup_row[row] = 1; }
+    C.assembly->copy(0, 2, 1, 9);   // a[2] = d[9]   (row 9 is odd: d is free there)
+    C.assembly->copy(2, 4, 1, 11);  // acc[4] = d[11]
+    const std::vector<Poly> fixed = C.fixed;
+    C.synth = [=](uint32_t phase, const std::vector<Fr>& ch, std::vector<Poly>& adv) {
+        if (phase == 0) {
+            Rng rng(seed * 131 + 9);
+            Poly &A = adv[0], &B = adv[1];
+            A.assign(n, f_zero());
+            B.assign(n, f_zero());
+            for (uint64_t row = 0; row < u; ++row) {
+                if (forced[row]) { A[row] = B[row - 1]; B[row] = A[row - 1]; continue; }
+                if (lookup_row[row]) {
+                    const uint64_t j = 1 + rng.next() % T;
+                    A[row] = f_u64(j);
+                    B[row] = f_u64(j * j + 1);
+                } else {
+                    A[row] = rng.fr();
+                    B[row] = rng.fr();
+                }
+            }
+            if (sabotage == 3) B[5] = f_add(B[5], f_one());    // lookup row 5: (a, b) is not a table row any more
+            if (sabotage == 4) B[4] = f_add(B[4], f_one());    // q_pair row 3: breaks ONLY b(wX) = a, the part weighted with s
+        } else {
+            const Fr r = ch[0];
+            const Poly &A = adv[0], &B = adv[1];
+            Poly &ACC = adv[2], &D = adv[3];
+            ACC.assign(n, f_zero());
+            D.assign(n, f_zero());
+            ACC[0] = A[0];
+            for (uint64_t row = 1; row < u; ++row) ACC[row] = f_add(f_mul(ACC[row - 1], r), A[row]);
+            for (uint64_t row = 0; row < u; row += 2) D[row] = f_add(f_mul(A[row], B[row]), r);
+            D[9] = A[2];
+            D[11] = ACC[4];
+            if (sabotage == 1) ACC[6] = f_add(ACC[6], f_one());  // breaks the running combination (provable, not acceptable)
+            if (sabotage == 2) D[9] = f_add(D[9], f_one());      // breaks the copy a[2] = d[9]
+            adv[0][1] = f_zero();                                  // a write to a committed column is discarded by create_proof
+        }
+    };
+    return C;
+}
+
 static std::string hex(const std::vector<uint8_t>& v) {
     static const char* d = "0123456789abcdef";
     std::string s;
@@ -204,7 +288,11 @@ int main(int argc, char** argv) {
     const uint64_t seed = argc > 3 ? (uint64_t)std::atoll(argv[3]) : 1;
     const int variant = argc > 4 ? std::atoi(argv[4]) : 1;
     const uint64_t n = 1ull << k;
-    auto build_any = [&](int sabotage) { return variant == 2 ? build_wide(k, seed, sabotage) : build(k, seed, sabotage); };
+    auto build_any = [&](int sabotage) { return variant == 3 ? build_phased(k, seed, sabotage) : (variant == 2 ? build_wide(k, seed, sabotage) : build(k, seed, sabotage)); };
+    // create_proof with the circuit's witness: known up front (variants 1, 2) or produced phase by phase from the challenges (3)
+    auto prove = [&](Ops& ops, const EvaluationDomain& dom, const ProvingKey& pk, const Circuit& C, uint64_t rng_seed, TranscriptKind kind) {
+        return C.synth ? create_proof(ops, dom, pk, C.synth, C.instances, rng_seed, kind) : create_proof(ops, dom, pk, C.advice, C.instances, rng_seed, kind);
+    };
     if (mode == "device") {
         // device only, at a size where the oracle would take minutes: SRS generated on the device, keygen + create_proof through the C
         // ABI with the Poseidon transcript, verified by the halo2-style verifier AND by the snark-verifier mirror under the exported
@@ -224,7 +312,7 @@ int main(int argc, char** argv) {
             vp.s_g2 = pairing::g2_mul(vp.g2, limbs);
             DeviceOps dops(params, dom);
             ProvingKey pk = keygen(dops, dom, C.cs, C.fixed, *C.assembly);
-            ProofArtifacts pr = create_proof(dops, dom, pk, C.advice, C.instances, 0xB200 + seed, TranscriptKind::Poseidon);
+            ProofArtifacts pr = prove(dops, dom, pk, C, 0xB200 + seed, TranscriptKind::Poseidon);
             std::string why;
             REQUIRE(verify_proof(dom, pk.vk, vp, C.instances, pr.proof, &why, TranscriptKind::Poseidon));
             protocol::PlonkProtocol P = protocol::parse_protocol(export_protocol_json(dom, pk.vk));
@@ -246,6 +334,7 @@ int main(int argc, char** argv) {
         Circuit C = build_any(0);
         if (variant == 1) REQUIRE(C.cs.degree() == 5 && C.cs.blinding_factors() == 5 && C.cs.permutation_chunk_len() == 3);
         if (variant == 2) REQUIRE(C.cs.degree() == 5 && C.cs.permutation_chunk_len() == 3 && C.cs.lookups.size() == 2 && C.cs.permutation.size() == 7);
+        if (variant == 3) REQUIRE(C.cs.degree() == 5 && C.cs.blinding_factors() == 5 && C.cs.num_phases() == 2 && C.cs.challenge_phase.size() == 2);
         EvaluationDomain dom = EvaluationDomain::new_(C.cs.degree(), k);
         REQUIRE(dom.extended_k == k + 2 && dom.quotient_poly_degree == 4);
 
@@ -266,7 +355,7 @@ int main(int argc, char** argv) {
 
         oracle_ops::OracleOps oops(g, gl, C.cs.degree(), k);
         ProvingKey pk_o = keygen(oops, dom, C.cs, C.fixed, *C.assembly);
-        ProofArtifacts po = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB200 + seed);
+        ProofArtifacts po = prove(oops, dom, pk_o, C, 0xB200 + seed, TranscriptKind::Blake2b);
         std::printf("proof_bytes %zu commitments %zu evals %zu\n", po.proof.size(), po.n_commitments, po.n_evals);
         REQUIRE(po.proof.size() == 32 * (po.n_commitments + po.n_evals));
         if (variant == 2) REQUIRE(po.n_commitments == 4 + 2 + 3 + 2 + 1 + 4 + 2);  // advice, m x2, z x3, phi x2, random, h x4, SHPLONK x2
@@ -300,7 +389,7 @@ int main(int argc, char** argv) {
             Circuit B = build_any(sabotage);
             bool accepted = false;
             try {
-                ProofArtifacts pb = create_proof(oops, dom, pk_o, B.advice, B.instances, 0xB200 + seed);
+                ProofArtifacts pb = prove(oops, dom, pk_o, B, 0xB200 + seed, TranscriptKind::Blake2b);
                 accepted = verify_proof(dom, pk_o.vk, vp, B.instances, pb.proof, &why);
             } catch (const Panic&) {
                 accepted = false;
@@ -308,12 +397,12 @@ int main(int argc, char** argv) {
             REQUIRE(!accepted);
         }
         // a different blinding seed gives a different, equally valid proof (zero-knowledge rows are really used)
-        ProofArtifacts po2 = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB201 + seed);
+        ProofArtifacts po2 = prove(oops, dom, pk_o, C, 0xB201 + seed, TranscriptKind::Blake2b);
         REQUIRE(po2.proof != po.proof && verify_proof(dom, pk_o.vk, vp, C.instances, po2.proof, &why));
 
         {   // ---- the reference's transcript: the same prover with snark-verifier's Poseidon transcript, and the protocol description a
             // snark-verifier-style verifier needs (checked by tests/test_plonk_session.py with the model that accepts the reference's proofs)
-            ProofArtifacts pp = create_proof(oops, dom, pk_o, C.advice, C.instances, 0xB200 + seed, TranscriptKind::Poseidon);
+            ProofArtifacts pp = prove(oops, dom, pk_o, C, 0xB200 + seed, TranscriptKind::Poseidon);
             REQUIRE(pp.proof.size() == po.proof.size() && pp.proof != po.proof);
             REQUIRE(verify_proof(dom, pk_o.vk, vp, C.instances, pp.proof, &why, TranscriptKind::Poseidon));
             REQUIRE(!verify_proof(dom, pk_o.vk, vp, C.instances, pp.proof, &why, TranscriptKind::Blake2b));  // the transcripts are not interchangeable
@@ -340,7 +429,7 @@ int main(int argc, char** argv) {
                 params2.k = k; params2.n = n; params2.g = g; params2.g_lagrange = gl;
                 DeviceOps dops2(params2, dom);
                 ProvingKey pk_d2 = keygen(dops2, dom, C.cs, C.fixed, *C.assembly);
-                ProofArtifacts pdp = create_proof(dops2, dom, pk_d2, C.advice, C.instances, 0xB200 + seed, TranscriptKind::Poseidon);
+                ProofArtifacts pdp = prove(dops2, dom, pk_d2, C, 0xB200 + seed, TranscriptKind::Poseidon);
                 std::printf("poseidon_proof device %s\n", hex(pdp.proof).c_str());
                 REQUIRE(pdp.proof == pp.proof);
             }
@@ -354,7 +443,7 @@ int main(int argc, char** argv) {
             REQUIRE(pk_d.vk.transcript_repr == pk_o.vk.transcript_repr);  // same fixed / permutation commitments
             for (size_t i = 0; i < pk_o.fixed_cosets.size(); ++i) REQUIRE(pk_d.fixed_cosets[i] == pk_o.fixed_cosets[i]);
             REQUIRE(pk_d.l_active_row == pk_o.l_active_row && pk_d.sigma_cosets == pk_o.sigma_cosets);
-            ProofArtifacts pd = create_proof(dops, dom, pk_d, C.advice, C.instances, 0xB200 + seed);
+            ProofArtifacts pd = prove(dops, dom, pk_d, C, 0xB200 + seed, TranscriptKind::Blake2b);
             std::printf("proof_sha_input device %s\n", hex(pd.proof).c_str());
             REQUIRE(pd.proof == po.proof);  // IDENTICAL PROOF BYTES: CUDA path == restated reference arithmetic
             REQUIRE(verify_proof(dom, pk_d.vk, vp, C.instances, pd.proof, &why));

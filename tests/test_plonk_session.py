@@ -17,9 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_plonk_session.cpp")
 BIN = os.path.join(ROOT, "tests", "cpp", "test_plonk_session")
 DIGESTS = os.path.join(ROOT, "tests", "golden", "plonk_session_digests.json")
-CASES = [(6, 1, 1), (7, 3, 1), (6, 1, 2), (7, 4, 2)]  # (k, seed, circuit variant: 1 = instance + one lookup + two permutation sets,
-#                                                          2 = "wide": two lookups (one two-column), three permutation sets, rotation -1)
-SHAPE = {1: "proof_bytes 1216 commitments 14 evals 24", 2: "proof_bytes 1760 commitments 18 evals 37"}
+CASES = [(6, 1, 1), (7, 3, 1), (6, 1, 2), (7, 4, 2), (6, 1, 3), (7, 2, 3)]
+# (k, seed, circuit variant): 1 = instance + one lookup + two permutation sets,
+#                             2 = "wide": two lookups (one two-column), three permutation sets, rotation -1
+#                             3 = "phased": two advice phases with a challenge each (running random linear combination, a lookup
+#                                 whose input and table are combined with the challenge, a copy from a phase-0 into a phase-1 cell)
+SHAPE = {1: "proof_bytes 1216 commitments 14 evals 24", 2: "proof_bytes 1760 commitments 18 evals 37",
+         3: "proof_bytes 1184 commitments 14 evals 23"}
+GPU_CASES = CASES + [(9, 5, 1), (8, 2, 2)]
 
 
 def binary():
@@ -56,7 +61,7 @@ def parse_poseidon(out):
     return proofs, proto_text, instances, ((w[0], w[1]), (w[2], w[3]))
 
 
-@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2)])
+@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2), (6, 1, 3)])
 def test_poseidon_transcript_proofs_are_accepted_by_the_snark_verifier_model(k, seed, variant, tmp_path):
     """create_proof with snark-verifier's Poseidon transcript + export_protocol_json: the proof is accepted by
     tests/snark_verifier_model.py -- the model that accepts the REFERENCE's shipped chunk and batch proofs
@@ -71,7 +76,9 @@ def test_poseidon_transcript_proofs_are_accepted_by_the_snark_verifier_model(k, 
     decide = lambda lhs, rhs: pairing_check([(lhs, G2_GEN), (rhs, g2_neg(s_g2))])
     lhs, rhs, info = verify_plonk(proto, instances, proof, spec)
     assert decide(lhs, rhs)
-    assert proto["num_witness"] == ([3, 1, 4] if variant == 1 else [4, 2, 6]) and proto["num_challenge"] == [1, 2, 1]
+    # per phase: advice commitments | challenges (theta joins the last phase), then [m] | [beta, gamma], [z, phi, random] | [y]
+    assert (proto["num_witness"], proto["num_challenge"]) == {1: ([3, 1, 4], [1, 2, 1]), 2: ([4, 2, 6], [1, 2, 1]),
+                                                             3: ([2, 2, 1, 3], [1, 2, 2, 1])}[variant]
     for pos in (7, len(proof) // 2, len(proof) - 9):
         bad = bytearray(proof)
         bad[pos] ^= 1
@@ -105,7 +112,7 @@ def test_session_over_the_oracle_verifies_and_matches_the_committed_digest(k, se
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,seed,variant", CASES + [(9, 5, 1), (8, 2, 2)])
+@pytest.mark.parametrize("k,seed,variant", GPU_CASES)
 def test_session_on_the_device_gives_identical_proof_bytes(k, seed, variant):
     proofs, out = run("both", k, seed, variant)
     assert "device proof identical to the oracle's" in out
@@ -118,7 +125,7 @@ def test_session_on_the_device_gives_identical_proof_bytes(k, seed, variant):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,variant", [(14, 1), (16, 2)])
+@pytest.mark.parametrize("k,variant", [(14, 1), (16, 2), (14, 3)])
 def test_device_only_session_at_larger_sizes_is_accepted_by_both_verifiers(k, variant):
     """2^14 / 2^16 rows (extended domain 2^16 / 2^18): SRS, keygen and create_proof entirely through the C ABI, Poseidon transcript;
     the pairing-based verifiers (halo2-style and the snark-verifier mirror under the exported protocol) accept, a flipped byte is

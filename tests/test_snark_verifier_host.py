@@ -84,7 +84,7 @@ def test_tampering_is_rejected(tmp_path):
     assert verdict(tmp_path, proto, proof, instances) == "ACCEPT"
 
 
-@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2)])
+@pytest.mark.parametrize("k,seed,variant", [(6, 1, 1), (7, 4, 2), (7, 2, 3)])
 def test_our_own_poseidon_proofs_are_accepted_under_the_exported_protocol(tmp_path, k, seed, variant):
     import test_plonk_session as TS
 
