@@ -15,7 +15,8 @@
 // BYTES from both.  The host keeps what upstream keeps on the host: the transcript, challenge arithmetic, blinding rows,
 // multiplicity counting, rotation-set bookkeeping.  The verifier is host-only (pairing_bn254.hpp), as in the reference.
 //
-// Fidelity: argument order, constraint order, y-folding, evaluation order and the SHPLONK construction follow upstream;
+// Fidelity: the phase loop (advice columns and challenges per phase, ConstraintSystem::{advice_column_phase, challenge_phase}),
+// argument order, constraint order, y-folding, evaluation order and the SHPLONK construction follow upstream;
 // `VerifyingKey::transcript_repr` is our own pinning (upstream hashes the Debug rendering of its Rust structs) and no
 // reference proof of a known circuit + SRS exists offline, so byte-compatibility WITH UPSTREAM PROOFS is not claimed
 // ("parity unpinned" at that level); what is tested is: proofs verify under an independent pairing check, device and
