@@ -273,7 +273,8 @@ def verify_plonk(protocol: dict, instances, proof: bytes, spec: PoseidonSpec):
     evals[(quotient_poly, 0)] = quotient_eval
     commitments = preprocessed + [None] * n_inst + witnesses
     zn_c = pow(zn, protocol["quotient"]["chunk_degree"], P)
-    commitments.append(msm([(pow(zn_c, i, P), q) for i, q in enumerate(quotients)]))
+    quotient_terms = [(pow(zn_c, i, P), q) for i, q in enumerate(quotients)]
+    commitments.append(msm(quotient_terms))
 
     # ---- Bdfg21
     polys_order, per_poly = [], {}
@@ -324,4 +325,7 @@ def verify_plonk(protocol: dict, instances, proof: bytes, spec: PoseidonSpec):
     terms.append((-z_s[0] % P, w))
     f = msm(terms)
     lhs = g1_add(f, g1_mul(w_prime, z_prime)) if z_prime else f
-    return lhs, w_prime, {"challenges": challenges, "z": z, "mu": mu, "gamma": gamma, "z_prime": z_prime, "n_sets": len(sets)}
+    # msm_terms / quotient_terms: the two multi-scalar multiplications of this verification as (scalar, point) lists, so that a test
+    # can redo them with another MSM implementation (f = msm(msm_terms) is the opening's left-hand side before + z' W')
+    return lhs, w_prime, {"challenges": challenges, "z": z, "mu": mu, "gamma": gamma, "z_prime": z_prime, "n_sets": len(sets),
+                          "msm_terms": terms, "quotient_terms": quotient_terms, "f": f}

@@ -106,3 +106,38 @@ def test_tampered_proofs_and_instances_are_rejected_and_the_product_pairing_agre
     wrong[0][20] ^= 1  # a public-input byte
     l3, r3, _ = verify_plonk(proto, wrong, proof, SPEC)
     assert not decide(l3, r3)
+
+
+def test_oracle_multiexp_redoes_the_msms_of_real_proofs_and_the_reference_srs_accepts_the_result():
+    """A known-answer test of MSM OUTPUTS on the reference's real data: the two multi-scalar multiplications inside the verification
+    of a shipped proof -- the quotient commitment sum_i z^(n i) h_i and the SHPLONK left-hand side over ALL of the proof's and the
+    verifying key's commitments with the transcript-derived scalars (15 terms for the thin chunk proofs) -- are recomputed by the ORACLE's best_multiexp
+    (oracle/halo2_arith.c, the restatement every CUDA result is compared with).  The result must be the model's point and, what no
+    implementation can fake by agreeing with another, must be accepted by the pairing against the trusted setup's -[s]G2."""
+    import numpy as np
+
+    from oracle import oracle as O
+    from pairing_model import g1_add, g1_mul
+
+    def oracle_msm(pairs, threads):
+        coeffs = np.stack([O.fr_from_int(s) for s, _ in pairs])
+        bases = np.stack([np.concatenate([O.fq_from_int(p[0]), O.fq_from_int(p[1])]) for _, p in pairs])
+        a = O.g1_to_affine(O.best_multiexp(coeffs, bases, threads=threads))
+        return O.fq_to_int(a[:4]), O.fq_to_int(a[4:])
+
+    picks = [decode(json.load(open(os.path.join(DATA, "full_proof_1.json")))["chunk_proofs"][0]),
+             decode(chunk_entries()[5][2]),
+             decode(json.load(open(os.path.join(DATA, "full_proof_batch_agg_1.json"))))]
+    for proto, proof, instances in picks:
+        lhs, rhs, info = verify_plonk(proto, instances, proof, SPEC)
+        terms = info["msm_terms"]
+        assert len(terms) >= 12 and all(p is not None for _, p in terms)
+        for threads in (1, 4):
+            f = oracle_msm(terms, threads)
+            assert f == info["f"]
+            assert decide(g1_add(f, g1_mul(rhs, info["z_prime"])), rhs)
+        q = oracle_msm(info["quotient_terms"], 1)
+        assert q == terms[[i for i, (_, p) in enumerate(terms) if p == q][0]][1]  # the quotient commitment is one of the bases
+        bad = list(terms)
+        bad[7] = ((bad[7][0] + 1) % (1 << 253), bad[7][1])
+        assert not decide(g1_add(oracle_msm(bad, 1), g1_mul(rhs, info["z_prime"])), rhs)
