@@ -722,6 +722,19 @@ inline ProvingKey keygen(Ops& ops, const EvaluationDomain& dom, ConstraintSystem
     if (cs.advice_queries.empty() && cs.fixed_queries.empty()) cs.finalize();
     const uint64_t n = dom.n;
     if (fixed.size() != cs.num_fixed) throw Panic("keygen: wrong number of fixed columns");
+    if (!cs.advice_phase.empty() && cs.advice_phase.size() != cs.num_advice) throw Panic("keygen: one phase per advice column");
+    {   // every Expression::Challenge names a declared challenge
+        std::function<void(const Expr&)> check = [&](const Expr& e) {
+            if (e.kind == Expr::Challenge && e.col >= cs.challenge_phase.size()) throw Panic("keygen: expression uses an undeclared challenge");
+            if (e.a) check(*e.a);
+            if (e.b) check(*e.b);
+        };
+        for (auto& g : cs.gates) check(*g);
+        for (auto& l : cs.lookups) {
+            for (auto& e : l.inputs) check(*e);
+            for (auto& e : l.table) check(*e);
+        }
+    }
     if (cs.degree() - 1 > dom.quotient_poly_degree) throw Panic("keygen: the domain's quotient degree is too small for this constraint system");
     ProvingKey pk;
     pk.vk.k = dom.k;
