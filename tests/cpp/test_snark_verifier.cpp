@@ -2,11 +2,14 @@
 //   {"protocol": <protocol JSON object>, "proof": "<hex>", "instances": [["<32-byte big-endian hex>", ...], ...],
 //    "s_g2": ["x_c1", "x_c0", "y_c1", "y_c0"]  (big-endian hex, EIP-197 word order; g2 is the generator)}
 // prints ACCEPT or REJECT <reason>.
+//   --file <proof file> <s_g2 x_c1> <x_c0> <y_c1> <y_c0>: a file AS THE REFERENCE WRITES IT (proof_files.hpp: a chunk / batch proof object
+//   or a container with "chunk_proofs"); one line per proof object, `ACCEPT chunk|batch k=.. proof_bytes=.. git=..` or `REJECT <reason>`,
+//   then `accepted <a> of <n>`; `--tamper` as a 7th argument flips one byte of every proof first.
 #include <cstdio>
 #include <fstream>
 #include <sstream>
 
-#include "../../scroll-prover_b200/snark_verifier_b200.hpp"
+#include "../../scroll-prover_b200/proof_files.hpp"
 
 using namespace halo2_b200;
 
@@ -20,8 +23,50 @@ static std::vector<uint8_t> unhex(const std::string& h) {
     return out;
 }
 
+static int verify_file(int argc, char** argv) {
+    try {
+        std::ifstream f(argv[2], std::ios::binary);
+        if (!f) {
+            std::printf("REJECT cannot open %s\n", argv[2]);
+            return 0;
+        }
+        std::stringstream ss;
+        ss << f.rdbuf();
+        uint8_t g2w[128];
+        for (int i = 0; i < 4; ++i) {
+            std::vector<uint8_t> w = unhex(argv[3 + i]);
+            if (w.size() != 32) return 2;
+            std::memcpy(g2w + 32 * i, w.data(), 32);
+        }
+        pairing::G2Point s_g2;
+        if (!pairing::g2_from_eip197(g2w, &s_g2) || !pairing::g2_on_curve(s_g2)) {
+            std::printf("REJECT malformed s_g2\n");
+            return 0;
+        }
+        const bool tamper = argc > 7 && std::string(argv[7]) == "--tamper";
+        std::vector<proof_files::ProofEntry> entries = proof_files::parse_file(ss.str());
+        size_t accepted = 0;
+        for (auto& e : entries) {
+            if (tamper) e.proof[e.proof.size() / 3] ^= 0x10;
+            std::string why;
+            if (proof_files::verify_entry(e, pairing::g2_generator(), s_g2, &why)) {
+                ++accepted;
+                std::printf("ACCEPT %s k=%u proof_bytes=%zu git=%s\n", e.is_chunk ? "chunk" : "batch", e.protocol.domain.k, e.proof.size(), e.git_version.c_str());
+            } else {
+                std::printf("REJECT %s\n", why.c_str());
+            }
+        }
+        std::printf("accepted %zu of %zu\n", accepted, entries.size());
+        return 0;
+    } catch (const std::exception& e) {
+        std::printf("REJECT exception: %s\n", e.what());
+        return 0;
+    }
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
+    if (std::string(argv[1]) == "--file") return argc >= 7 ? verify_file(argc, argv) : 2;
     try {
         std::ifstream f(argv[1], std::ios::binary);
         std::stringstream ss;

@@ -28,7 +28,7 @@ S_G2 = (NEG_S_G2[0], ((-NEG_S_G2[1][0]) % Q, (-NEG_S_G2[1][1]) % Q))
 
 
 def binary():
-    deps = [SRC] + [os.path.join(ROOT, "scroll-prover_b200", h) for h in ("snark_verifier_b200.hpp", "plonk_b200.hpp", "protocol_json.hpp", "pairing_bn254.hpp")]
+    deps = [SRC] + [os.path.join(ROOT, "scroll-prover_b200", h) for h in ("snark_verifier_b200.hpp", "proof_files.hpp", "plonk_b200.hpp", "protocol_json.hpp", "pairing_bn254.hpp", "serde_bn254.hpp")]
     if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
         lib = os.path.join(ROOT, "scroll-prover_b200")
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", BIN, SRC, "-L" + lib, "-lb200zk", "-Wl,-rpath," + lib])
@@ -95,3 +95,48 @@ def test_our_own_poseidon_proofs_are_accepted_under_the_exported_protocol(tmp_pa
     bad = bytearray(proof)
     bad[len(bad) // 3] ^= 1
     assert verdict(tmp_path, proto, bytes(bad), instances, s_g2=s_g2).startswith("REJECT")
+
+
+def verify_file(path, s_g2=S_G2, tamper=False):
+    r = subprocess.run([binary(), "--file", str(path)] + g2_words(s_g2) + (["--tamper"] if tamper else []), capture_output=True, text=True, timeout=600)
+    lines = r.stdout.strip().splitlines()
+    accepted, total = int(lines[-1].split()[1]), int(lines[-1].split()[3])
+    return accepted, total, lines[:-1]
+
+
+@have_ref
+def test_every_proof_file_the_reference_ships_is_read_and_accepted():
+    """scroll-prover_b200/proof_files.hpp reads the reference's proof files AS WRITTEN (serde_json objects with base64 fields, the
+    chunk_proofs containers of batch tasks) and runs verify_chunk_proof / verify_batch_proof on every proof object in them: all 319
+    distinct chunk proofs of the batch tasks and both batch proofs are accepted -- the protocol they carry, the proof, the carried
+    accumulator, and the vk bytes beside them matching the protocol's preprocessed commitments."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(DATA, "*.json"))) + sorted(glob.glob(os.path.join(DATA, "batch_tasks", "*.json")))
+    chunk = batch = 0
+    for f in files:
+        accepted, total, lines = verify_file(f)
+        assert accepted == total and total >= 1, (f, [l for l in lines if not l.startswith("ACCEPT")][:3])
+        chunk += sum(1 for l in lines if l.startswith("ACCEPT chunk k=25 proof_bytes=896"))
+        batch += sum(1 for l in lines if l.startswith("ACCEPT batch k=26"))
+    assert (chunk, batch) == (319, 2)
+
+
+@have_ref
+def test_proof_files_with_a_flipped_proof_byte_or_another_setup_are_rejected(tmp_path):
+    f = os.path.join(DATA, "batch-task-with-blob-raw.json")
+    assert verify_file(f)[:2] == (4, 4)
+    assert verify_file(f, tamper=True)[:2] == (0, 4)
+    assert verify_file(f, s_g2=NEG_S_G2)[:2] == (0, 4)
+    # a vk that belongs to another circuit beside the proof: refused before any pairing
+    j = json.load(open(os.path.join(DATA, "full_proof_1.json")))
+    j["chunk_proofs"][0]["vk"] = json.load(open(os.path.join(DATA, "full_proof_batch_agg_1.json")))["vk"]
+    p = tmp_path / "swapped_vk.json"
+    p.write_text(json.dumps(j))
+    accepted, total, lines = verify_file(p)
+    assert (accepted, total) == (0, 1) and "vk" in lines[0]
+    # malformed base64 is an error, not a crash
+    j["chunk_proofs"][0]["vk"] = "@@@@"
+    p.write_text(json.dumps(j))
+    r = subprocess.run([binary(), "--file", str(p)] + g2_words(S_G2), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("REJECT exception")
