@@ -9,8 +9,14 @@
 //     (test_data/batch-task-*.json, batch_tasks/*.json) or a dumped chunk-proof list (full_proof_1.json).
 // With snark_verifier_b200.hpp this is `ChunkVerifier::verify_chunk_proof` / `BatchVerifier::verify_batch_proof` on the reference's own
 // files: verify_entry() checks the proof under the protocol it carries, the accumulator it carries forward, and that the verifying
-// key bytes beside it hold exactly the protocol's preprocessed commitments (same circuit).  Host-only, header-only.
+// key bytes beside it hold exactly the protocol's preprocessed commitments (same circuit).  A chunk proof's public input is bound to
+// its `chunk_info` as well: instances[12..44] are the 32 bytes of
+//   keccak256(chain_id as u64 BE || prev_state_root || post_state_root || withdraw_root || data_hash || keccak256(tx_bytes))
+// (`ChunkInfo::public_input_hash`, crate `aggregator` of scroll-tech/zkevm-circuits @ 7fd6b6d, /root/reference/Cargo.lock:32-34 -- an
+// un-vendored dependency; the formula is anchored on the reference's data: it reproduces the public input of all 319 chunk proofs
+// under integration/tests/test_data).  Host-only, header-only.
 #pragma once
+#include <array>
 #include <string>
 #include <vector>
 
@@ -51,12 +57,83 @@ inline std::vector<uint8_t> base64_decode(const std::string& s) {
     return out;
 }
 
+// Keccak-256 (the pre-standard padding 0x01 .. 0x80 Ethereum uses), for the chunk public-input hash
+inline std::array<uint8_t, 32> keccak256(const uint8_t* data, size_t len) {
+    static const uint64_t RC[24] = {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull, 0x8000000080008000ull, 0x000000000000808Bull,
+                                    0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008Aull, 0x0000000000000088ull,
+                                    0x0000000080008009ull, 0x000000008000000Aull, 0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull,
+                                    0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull, 0x800000008000000Aull,
+                                    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+    static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};  // [x + 5 y]
+    uint64_t a[25] = {0};
+    auto rol = [](uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; };
+    auto permute = [&]() {
+        for (int round = 0; round < 24; ++round) {
+            uint64_t c[5], b[25];
+            for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+            for (int x = 0; x < 5; ++x) {
+                uint64_t d = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
+                for (int y = 0; y < 5; ++y) a[x + 5 * y] ^= d;
+            }
+            for (int x = 0; x < 5; ++x)
+                for (int y = 0; y < 5; ++y) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol(a[x + 5 * y], ROT[x + 5 * y]);
+            for (int x = 0; x < 5; ++x)
+                for (int y = 0; y < 5; ++y) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+            a[0] ^= RC[round];
+        }
+    };
+    const size_t rate = 136;
+    std::vector<uint8_t> msg(data, data + len);
+    msg.push_back(0x01);
+    while (msg.size() % rate) msg.push_back(0);
+    msg.back() |= 0x80;
+    for (size_t off = 0; off < msg.size(); off += rate) {
+        for (size_t i = 0; i < rate / 8; ++i) {
+            uint64_t w = 0;
+            for (int b = 7; b >= 0; --b) w = (w << 8) | msg[off + 8 * i + b];
+            a[i] ^= w;
+        }
+        permute();
+    }
+    std::array<uint8_t, 32> out;
+    for (int i = 0; i < 4; ++i)
+        for (int b = 0; b < 8; ++b) out[8 * i + b] = (uint8_t)(a[i] >> (8 * b));
+    return out;
+}
+
+struct ChunkInfo {  // the fields of a proof object's "chunk_info" that enter the public input
+    uint64_t chain_id = 0;
+    std::array<uint8_t, 32> prev_state_root{}, post_state_root{}, withdraw_root{}, data_hash{};
+    std::vector<uint8_t> tx_bytes;
+    std::array<uint8_t, 32> public_input_hash() const {
+        std::vector<uint8_t> pre;
+        for (int b = 7; b >= 0; --b) pre.push_back((uint8_t)(chain_id >> (8 * b)));
+        for (auto* f : {&prev_state_root, &post_state_root, &withdraw_root, &data_hash}) pre.insert(pre.end(), f->begin(), f->end());
+        const auto txh = keccak256(tx_bytes.data(), tx_bytes.size());
+        pre.insert(pre.end(), txh.begin(), txh.end());
+        return keccak256(pre.data(), pre.size());
+    }
+};
+
+inline std::array<uint8_t, 32> hex32(const std::string& h) {  // "0x" + 64 hex digits
+    if (h.size() != 66 || h[0] != '0' || h[1] != 'x') throw std::runtime_error("proof file: expected a 0x-prefixed 32-byte hex string");
+    std::array<uint8_t, 32> out;
+    auto nib = [](char c) -> int { return c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : (c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1)); };
+    for (int i = 0; i < 32; ++i) {
+        int hi = nib(h[2 + 2 * i]), lo = nib(h[3 + 2 * i]);
+        if (hi < 0 || lo < 0) throw std::runtime_error("proof file: not a hex digit");
+        out[i] = (uint8_t)(hi * 16 + lo);
+    }
+    return out;
+}
+
 struct ProofEntry {
     protocol::PlonkProtocol protocol;
     std::vector<uint8_t> proof, vk;
     std::vector<std::vector<Fr>> instances;  // one column
     std::string git_version;
     bool is_chunk = false;  // carries a chunk_info (chunk proof) rather than a batch_hash (batch proof)
+    ChunkInfo chunk_info;
 };
 
 inline ProofEntry parse_entry(const protocol::Json& e) {
@@ -78,6 +155,15 @@ inline ProofEntry parse_entry(const protocol::Json& e) {
     p.instances.push_back(col);
     if (e.has("git_version")) p.git_version = e.at("git_version").text;
     p.is_chunk = e.has("chunk_info");
+    if (p.is_chunk) {
+        const protocol::Json& ci = e.at("chunk_info");
+        p.chunk_info.chain_id = ci.at("chain_id").u64();
+        p.chunk_info.prev_state_root = hex32(ci.at("prev_state_root").text);
+        p.chunk_info.post_state_root = hex32(ci.at("post_state_root").text);
+        p.chunk_info.withdraw_root = hex32(ci.at("withdraw_root").text);
+        p.chunk_info.data_hash = hex32(ci.at("data_hash").text);
+        p.chunk_info.tx_bytes = base64_decode(ci.at("tx_bytes").text);
+    }
     return p;
 }
 
@@ -111,9 +197,19 @@ inline bool vk_matches_protocol(const ProofEntry& p, std::string* why = nullptr)
     return same;
 }
 
+// a chunk proof's public input: 12 accumulator limbs, then the 32 bytes of ChunkInfo::public_input_hash, one per instance cell
+inline bool chunk_info_matches_instances(const ProofEntry& p, std::string* why = nullptr) {
+    const auto h = p.chunk_info.public_input_hash();
+    bool same = p.is_chunk && p.instances.size() == 1 && p.instances[0].size() == 12 + 32;
+    for (int i = 0; same && i < 32; ++i) same = p.instances[0][12 + i] == plonk::f_u64(h[i]);
+    if (!same && why) *why = "the public input is not the hash of the chunk_info beside the proof";
+    return same;
+}
+
 // ChunkVerifier::verify_chunk_proof / BatchVerifier::verify_batch_proof on one proof object
 inline bool verify_entry(const ProofEntry& p, const pairing::G2Point& g2, const pairing::G2Point& s_g2, std::string* why = nullptr) {
     if (!vk_matches_protocol(p, why)) return false;
+    if (p.is_chunk && !chunk_info_matches_instances(p, why)) return false;
     return snark::verify(p.protocol, p.instances, p.proof, g2, s_g2, why);
 }
 

@@ -5,6 +5,7 @@
 //   --file <proof file> <s_g2 x_c1> <x_c0> <y_c1> <y_c0>: a file AS THE REFERENCE WRITES IT (proof_files.hpp: a chunk / batch proof object
 //   or a container with "chunk_proofs"); one line per proof object, `ACCEPT chunk|batch k=.. proof_bytes=.. git=..` or `REJECT <reason>`,
 //   then `accepted <a> of <n>`; `--tamper` as a 7th argument flips one byte of every proof first.
+//   --keccak <hex>: Keccak-256 of the message (proof_files.hpp's hash for the chunk public input).
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -67,6 +68,13 @@ static int verify_file(int argc, char** argv) {
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (std::string(argv[1]) == "--file") return argc >= 7 ? verify_file(argc, argv) : 2;
+    if (std::string(argv[1]) == "--keccak") {  // --keccak <hex message>: proof_files::keccak256, for the known-answer test
+        std::vector<uint8_t> msg = unhex(argc > 2 ? argv[2] : "");
+        auto d = proof_files::keccak256(msg.data(), msg.size());
+        for (uint8_t b : d) std::printf("%02x", b);
+        std::printf("\n");
+        return 0;
+    }
     try {
         std::ifstream f(argv[1], std::ios::binary);
         std::stringstream ss;

@@ -140,3 +140,29 @@ def test_proof_files_with_a_flipped_proof_byte_or_another_setup_are_rejected(tmp
     p.write_text(json.dumps(j))
     r = subprocess.run([binary(), "--file", str(p)] + g2_words(S_G2), capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.startswith("REJECT exception")
+
+
+def test_keccak256_of_the_proof_file_reader_known_answers():
+    from yul_verifier import keccak256
+
+    for msg in (b"", b"abc", bytes(range(135)), bytes(range(136)), bytes(range(200)) * 3):
+        out = subprocess.run([binary(), "--keccak", msg.hex()], capture_output=True, text=True, timeout=60).stdout.strip()
+        assert out == keccak256(msg).hex()
+    assert subprocess.run([binary(), "--keccak", ""], capture_output=True, text=True).stdout.strip() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+@have_ref
+def test_a_chunk_proof_is_bound_to_the_chunk_info_beside_it(tmp_path):
+    """instances[12..44] = keccak256(chain_id || prev_state_root || post_state_root || withdraw_root || data_hash || keccak256(tx_bytes)):
+    true for every shipped chunk proof (test_every_proof_file_... goes through the same check); any changed field is refused"""
+    j = json.load(open(os.path.join(DATA, "full_proof_1.json")))
+    p = tmp_path / "edited.json"
+    for field, edit in (("chain_id", lambda v: v + 1), ("post_state_root", lambda v: v[:-1] + ("0" if v[-1] != "0" else "1")),
+                        ("tx_bytes", lambda v: base64.b64encode(base64.b64decode(v) + b"\x00").decode())):
+        k = json.loads(json.dumps(j))
+        k["chunk_proofs"][0]["chunk_info"][field] = edit(k["chunk_proofs"][0]["chunk_info"][field])
+        p.write_text(json.dumps(k))
+        accepted, total, lines = verify_file(p)
+        assert (accepted, total) == (0, 1) and "chunk_info" in lines[0], field
+    p.write_text(json.dumps(j))
+    assert verify_file(p)[:2] == (1, 1)
