@@ -14,7 +14,8 @@
 //   keccak256(chain_id as u64 BE || prev_state_root || post_state_root || withdraw_root || data_hash || keccak256(tx_bytes))
 // (`ChunkInfo::public_input_hash`, crate `aggregator` of scroll-tech/zkevm-circuits @ 7fd6b6d, /root/reference/Cargo.lock:32-34 -- an
 // un-vendored dependency; the formula is anchored on the reference's data: it reproduces the public input of all 319 chunk proofs
-// under integration/tests/test_data).  Host-only, header-only.
+// under integration/tests/test_data).  A batch proof's `batch_hash` field is checked against its public input likewise.
+// Host-only, header-only.
 #pragma once
 #include <array>
 #include <string>
@@ -134,6 +135,8 @@ struct ProofEntry {
     std::string git_version;
     bool is_chunk = false;  // carries a chunk_info (chunk proof) rather than a batch_hash (batch proof)
     ChunkInfo chunk_info;
+    bool has_batch_hash = false;
+    std::array<uint8_t, 32> batch_hash{};
 };
 
 inline ProofEntry parse_entry(const protocol::Json& e) {
@@ -163,6 +166,10 @@ inline ProofEntry parse_entry(const protocol::Json& e) {
         p.chunk_info.withdraw_root = hex32(ci.at("withdraw_root").text);
         p.chunk_info.data_hash = hex32(ci.at("data_hash").text);
         p.chunk_info.tx_bytes = base64_decode(ci.at("tx_bytes").text);
+    }
+    if (e.has("batch_hash")) {
+        p.has_batch_hash = true;
+        p.batch_hash = hex32(e.at("batch_hash").text);
     }
     return p;
 }
@@ -206,10 +213,26 @@ inline bool chunk_info_matches_instances(const ProofEntry& p, std::string* why =
     return same;
 }
 
+// a batch proof's public input: 12 accumulator limbs, then 32-byte values as (high, low) 16-byte halves -- parent_state_root,
+// parent_batch_hash, current_state_root, batch_hash -- then chain_id and withdraw_root (high, low); the "batch_hash" field beside the
+// proof is cells 18 and 19 (layout read off the reference's two shipped batch proofs, whose second continues the first)
+inline bool batch_hash_matches_instances(const ProofEntry& p, std::string* why = nullptr) {
+    bool same = p.has_batch_hash && p.instances.size() == 1 && p.instances[0].size() == 12 + 11;
+    for (int half = 0; same && half < 2; ++half) {
+        uint8_t le[32] = {0};
+        for (int b = 0; b < 16; ++b) le[b] = p.batch_hash[16 * half + 15 - b];
+        Fr v;
+        same = plonk::f_from_repr(le, &v) && p.instances[0][18 + half] == v;
+    }
+    if (!same && why) *why = "the public input does not carry the batch_hash beside the proof";
+    return same;
+}
+
 // ChunkVerifier::verify_chunk_proof / BatchVerifier::verify_batch_proof on one proof object
 inline bool verify_entry(const ProofEntry& p, const pairing::G2Point& g2, const pairing::G2Point& s_g2, std::string* why = nullptr) {
     if (!vk_matches_protocol(p, why)) return false;
     if (p.is_chunk && !chunk_info_matches_instances(p, why)) return false;
+    if (p.has_batch_hash && !batch_hash_matches_instances(p, why)) return false;
     return snark::verify(p.protocol, p.instances, p.proof, g2, s_g2, why);
 }
 

@@ -166,3 +166,16 @@ def test_a_chunk_proof_is_bound_to_the_chunk_info_beside_it(tmp_path):
         assert (accepted, total) == (0, 1) and "chunk_info" in lines[0], field
     p.write_text(json.dumps(j))
     assert verify_file(p)[:2] == (1, 1)
+
+
+@have_ref
+def test_a_batch_proof_carries_its_batch_hash_and_the_second_continues_the_first(tmp_path):
+    b1, b2 = (json.load(open(os.path.join(DATA, f"full_proof_batch_agg_{i}.json"))) for i in (1, 2))
+    w1, w2 = decode(b1)[2][0], decode(b2)[2][0]
+    assert len(w1) == 23 and (w1[18] << 128) | w1[19] == int(b1["batch_hash"], 16) and (w2[18] << 128) | w2[19] == int(b2["batch_hash"], 16)
+    assert w2[12:16] == w1[16:20] and w1[20] == w2[20]  # parent state root / batch hash of #2 = current of #1; same chain id
+    p = tmp_path / "edited.json"
+    b1["batch_hash"] = b1["batch_hash"][:-1] + ("0" if b1["batch_hash"][-1] != "0" else "1")
+    p.write_text(json.dumps(b1))
+    accepted, total, lines = verify_file(p)
+    assert (accepted, total) == (0, 1) and "batch_hash" in lines[0]
