@@ -120,6 +120,16 @@ def test_every_proof_file_the_reference_ships_is_read_and_accepted():
         chunk += sum(1 for l in lines if l.startswith("ACCEPT chunk k=25 proof_bytes=896"))
         batch += sum(1 for l in lines if l.startswith("ACCEPT batch k=26"))
     assert (chunk, batch) == (319, 2)
+    # and every one of those chunk proofs was made for the RELEASED circuit: the vk and the protocol it carries are byte-for-byte
+    # release-v0.13.1/vk_chunk.vkey and chunk.protocol (four different git versions of the prover among them)
+    rel_vk = open("/root/reference/release-v0.13.1/vk_chunk.vkey", "rb").read()
+    rel_proto = json.load(open("/root/reference/release-v0.13.1/chunk.protocol"))
+    versions = set()
+    for f in files:
+        for cp in json.load(open(f)).get("chunk_proofs", []):
+            assert base64.b64decode(cp["vk"]) == rel_vk and json.loads(base64.b64decode(cp["protocol"])) == rel_proto
+            versions.add(cp["git_version"])
+    assert len(versions) == 4
 
 
 @have_ref
