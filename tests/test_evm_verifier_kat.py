@@ -161,3 +161,54 @@ def test_reference_verifier_bytecode_on_the_products_host_curve_and_pairing_code
     # a truncated proof is rejected as well (CALLDATALOAD past the end reads zeros: not a curve point / wrong pairing)
     ok3, _ = call(runtime, calldata[:-32], add, mul, pairing)
     assert not ok3
+
+
+# ---- the PRODUCT's EVMVerifier (scroll-prover_b200/evm_verifier_b200.hpp): the same bytecode on a C++ stack machine whose
+# precompiles are the product's host curve / pairing code -- /root/reference/integration/src/verifier.rs without an EVM
+EVM_SRC = os.path.join(ROOT, "tests", "cpp", "test_evm_verifier.cpp")
+EVM_BIN = os.path.join(ROOT, "tests", "cpp", "test_evm_verifier")
+
+
+def evm_binary():
+    deps = [EVM_SRC] + [os.path.join(ROOT, "scroll-prover_b200", h) for h in ("evm_verifier_b200.hpp", "keccak256.hpp", "pairing_bn254.hpp", "csrc/ec.cuh", "csrc/ff.cuh")]
+    if not os.path.exists(EVM_BIN) or any(os.path.getmtime(d) > os.path.getmtime(EVM_BIN) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", EVM_BIN, EVM_SRC])
+    return EVM_BIN
+
+
+def product_evm(*extra):
+    out = subprocess.run([evm_binary(), os.path.join(REL, "evm_verifier.bin"), os.path.join(REL, "proof.data"), os.path.join(REL, "pi.data"), *map(str, extra)],
+                         capture_output=True, text=True, timeout=120).stdout.split()
+    return out[0], dict(kv.split("=") for kv in out[1:])
+
+
+def test_the_products_evm_verifier_accepts_the_shipped_proof_like_the_python_machine():
+    from evm_bytecode import call, deploy
+
+    verdict, info = product_evm()
+    _, calldata = load()
+    ok, m = call(deploy(load_bin()), calldata, m_add, m_mul, m_pairing)
+    assert verdict == "ACCEPT" and ok
+    assert int(info["runtime_bytes"]) == 0x36A3 and int(info["steps"]) == m.steps  # instruction for instruction
+    assert (int(info["keccak"]), int(info["modexp"]), int(info["ecadd"]), int(info["ecmul"]), int(info["pairing"])) == \
+        (m.keccak_calls, m.precompile_calls[5], m.precompile_calls[6], m.precompile_calls[7], m.precompile_calls[8])
+    for pos in (40, 384 + 5, 800 + 5, 800 + 700, len(calldata) - 3):
+        assert product_evm(pos)[0] == "REJECT", pos
+    assert product_evm(-32)[0] == "REJECT"  # truncated
+
+
+def test_the_products_evm_word_arithmetic_matches_python_integers():
+    import random
+
+    rnd = random.Random(0xE7)
+    top = (1 << 256) - 1
+    R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    cases = [(0, 0, 0), (top, top, top), (top, top, 1), (top, 1, 0), (5, 3, 7), (top, top, Q), (Q - 1, Q - 1, Q), (R_MOD - 1, R_MOD - 2, R_MOD),
+             (1 << 255, 1 << 255, (1 << 255) + 1), (top, 255, top - 1), (1, 256, 0), (12345, 64, 1 << 200)]
+    cases += [(rnd.getrandbits(256), rnd.getrandbits(rnd.choice((8, 64, 256))), rnd.getrandbits(rnd.choice((1, 64, 255, 256)))) for _ in range(40)]
+    for a, b, m in cases:
+        out = subprocess.run([evm_binary(), "--arith", "%064x" % a, "%064x" % b, "%064x" % m], capture_output=True, text=True, timeout=60).stdout.split()
+        got = [int(x, 16) for x in out]
+        want = [(a + b) % m if m else 0, a * b % m if m else 0, a % m if m else 0, pow(a, b, m) if m else 0, (a + b) & top, (a - b) & top,
+                (a << b) & top if b < 256 else 0]
+        assert got == want, (hex(a), hex(b), hex(m))
