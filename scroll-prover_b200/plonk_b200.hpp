@@ -5,6 +5,7 @@
 //   plonk::{permutation, mv_lookup, vanishing} prover / verifier arguments               (src/plonk/*/{prover,verifier}.rs)
 //   poly::kzg::multiopen::{ProverSHPLONK, VerifierSHPLONK}                                (src/poly/kzg/multiopen/shplonk/*)
 //   transcript::{Blake2bWrite, Blake2bRead, Challenge255}                                 (src/transcript.rs)
+//   dev::MockProver (constraint check without proving)                                   (src/dev.rs)
 // of scroll-tech/halo2 @ e5ddf67 (pin /root/reference/Cargo.lock:1886-1888), the function the reference enters at
 // /root/reference/integration/src/prove.rs:37-39 (gen_halo2_chunk_proof) and checks at :50-53 (verify_chunk_proof).
 //
@@ -1261,6 +1262,75 @@ inline ProofArtifacts create_proof(Ops& ops, const EvaluationDomain& dom, const 
             if (cs.phase_of_advice(c) == phase) table[c] = advice[c];
     };
     return create_proof(ops, dom, pk, fill, instances, rng_seed, transcript_kind);
+}
+
+// ------------------------------------------------------------------------------------------------ MockProver (host only)
+// dev::MockProver::run + verify, the check the reference's `make mock` performs before any proving
+// (/root/reference/integration/src/mock.rs:11-30 -> MockProver::verify_par): the witness is synthesised phase by phase (challenges
+// from `seed` instead of a transcript), the rows beyond the usable ones are filled with random values as create_proof would blind
+// them, and every constraint is evaluated with plain field arithmetic -- no polynomial, no commitment, no device:
+//   gates on EVERY row of the domain (what the quotient identity demands; a selector that is live on a row whose rotations reach
+//   into the blinding rows shows up here), lookup inputs against the table on the usable rows, copy constraints cell by cell.
+struct MockFailure {
+    enum Kind { Gate, Lookup, Permutation } kind;
+    size_t index;  // gate index, lookup index, or index of the column in cs.permutation
+    uint64_t row;
+    bool operator==(const MockFailure& o) const { return kind == o.kind && index == o.index && row == o.row; }
+};
+inline std::vector<MockFailure> mock_prove(const EvaluationDomain& dom, ConstraintSystem cs, const std::vector<Poly>& fixed, const Assembly& assembly,
+                                           const WitnessFn& synthesize, const std::vector<Poly>& instances, uint64_t seed = 1) {
+    if (cs.advice_queries.empty() && cs.fixed_queries.empty()) cs.finalize();
+    const uint64_t n = dom.n, u = n - cs.blinding_factors() - 1;
+    if (fixed.size() != cs.num_fixed || instances.size() != cs.num_instance) throw Panic("mock_prove: wrong number of columns");
+    Rng rng(seed);
+    std::vector<Poly> advice(cs.num_advice, Poly(n, f_zero()));
+    std::vector<Fr> challenges(cs.challenge_phase.size(), f_zero());
+    for (uint32_t phase = 0; phase < cs.num_phases(); ++phase) {
+        std::vector<Poly> work = advice;
+        synthesize(phase, challenges, work);
+        for (uint32_t c = 0; c < cs.num_advice; ++c) {
+            if (cs.phase_of_advice(c) != phase) continue;
+            if (work[c].size() != n) throw Panic("mock_prove: advice column length");
+            advice[c] = std::move(work[c]);
+            for (uint64_t r = u; r < n; ++r) advice[c][r] = rng.fr();
+        }
+        for (size_t i = 0; i < challenges.size(); ++i)
+            if (cs.challenge_phase[i] == phase) challenges[i] = rng.fr();
+    }
+    const Fr theta = rng.fr();
+    auto cell = [&](uint64_t row) {
+        return [&, row](int kind, uint32_t col, int32_t rot) -> Fr {
+            if (kind == Expr::Challenge) return challenges[col];
+            const uint64_t r = (uint64_t)((((int64_t)row + rot) % (int64_t)n + (int64_t)n) % (int64_t)n);
+            return kind == Expr::Fixed ? fixed[col][r] : (kind == Expr::Advice ? advice[col][r] : instances[col][r]);
+        };
+    };
+    std::vector<MockFailure> failures;
+    for (size_t g = 0; g < cs.gates.size(); ++g)
+        for (uint64_t r = 0; r < n; ++r)
+            if (!f_is_zero(cs.gates[g]->eval_with(cell(r)))) failures.push_back({MockFailure::Gate, g, r});
+    for (size_t li = 0; li < cs.lookups.size(); ++li) {
+        auto compress = [&](const std::vector<ExprP>& es, uint64_t r) {
+            Fr acc = f_zero();
+            auto q = cell(r);
+            for (auto& e : es) acc = f_add(f_mul(acc, theta), e->eval_with(q));
+            return std::array<uint64_t, 4>{acc.l[0], acc.l[1], acc.l[2], acc.l[3]};
+        };
+        std::set<std::array<uint64_t, 4>> table;
+        for (uint64_t r = 0; r < u; ++r) table.insert(compress(cs.lookups[li].table, r));
+        for (uint64_t r = 0; r < u; ++r)
+            if (!table.count(compress(cs.lookups[li].inputs, r))) failures.push_back({MockFailure::Lookup, li, r});
+    }
+    auto value = [&](size_t pcol, uint64_t r) {
+        const Column& c = cs.permutation[pcol];
+        return c.kind == Expr::Fixed ? fixed[c.index][r] : (c.kind == Expr::Advice ? advice[c.index][r] : instances[c.index][r]);
+    };
+    for (size_t c = 0; c < cs.permutation.size(); ++c)
+        for (uint64_t r = 0; r < n; ++r) {
+            const auto next = assembly.mapping[c][r];
+            if (!(value(c, r) == value(next.first, next.second))) failures.push_back({MockFailure::Permutation, c, r});
+        }
+    return failures;
 }
 
 // ------------------------------------------------------------------------------------------------ snark-verifier protocol export

@@ -106,6 +106,7 @@ def key(k, seed, variant):
 @pytest.mark.parametrize("k,seed,variant", CASES)
 def test_session_over_the_oracle_verifies_and_matches_the_committed_digest(k, seed, variant):
     proofs, out = run("oracle", k, seed, variant)
+    assert "mock_prove: honest witness clean; sabotaged witnesses flagged" in out  # dev::MockProver's check, no proving
     assert SHAPE[variant] in out  # variant 1: 3 advice + m + 2 z + phi + random + 4 h + 2 SHPLONK points
     want = json.load(open(DIGESTS))[key(k, seed, variant)]
     assert hashlib.sha256(proofs["oracle"]).hexdigest() == want
