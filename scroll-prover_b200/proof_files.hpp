@@ -75,8 +75,9 @@ struct ChunkInfo {  // the fields of a proof object's "chunk_info" that enter th
     }
 };
 
-inline std::array<uint8_t, 32> hex32(const std::string& h) {  // "0x" + 64 hex digits
-    if (h.size() != 66 || h[0] != '0' || h[1] != 'x') throw std::runtime_error("proof file: expected a 0x-prefixed 32-byte hex string");
+inline std::array<uint8_t, 32> hex32(const std::string& h0) {  // 64 hex digits, with or without "0x" (the reference's files hold both)
+    const std::string h = h0.size() == 64 ? "0x" + h0 : h0;
+    if (h.size() != 66 || h[0] != '0' || h[1] != 'x') throw std::runtime_error("proof file: expected a 32-byte hex string");
     std::array<uint8_t, 32> out;
     auto nib = [](char c) -> int { return c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : (c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1)); };
     for (int i = 0; i < 32; ++i) {
@@ -85,6 +86,58 @@ inline std::array<uint8_t, 32> hex32(const std::string& h) {  // "0x" + 64 hex d
         out[i] = (uint8_t)(hi * 16 + lo);
     }
     return out;
+}
+
+inline ChunkInfo parse_chunk_info(const protocol::Json& ci) {
+    ChunkInfo c;
+    c.chain_id = ci.at("chain_id").u64();
+    c.prev_state_root = hex32(ci.at("prev_state_root").text);
+    c.post_state_root = hex32(ci.at("post_state_root").text);
+    c.withdraw_root = hex32(ci.at("withdraw_root").text);
+    c.data_hash = hex32(ci.at("data_hash").text);
+    c.tx_bytes = base64_decode(ci.at("tx_bytes").text);
+    return c;
+}
+
+// the "batch_header" of a batch proving task.  batch_hash = keccak256 of its 193-byte encoding
+//   version (1) | batch_index | l1_message_popped | total_l1_message_popped (8 each, BE) | data_hash | blob_versioned_hash |
+//   parent_batch_hash (32 each) | last_block_timestamp (8, BE) | blob_data_proof (2 x 32)
+// (`BatchHeader::batch_hash`, crate `aggregator`, same pin as above).  Anchored on the reference's data: the header of
+// test_data/full_proof_batch_prove_1.json hashes to the `batch_hash` of full_proof_batch_agg_1.json, and the ten consecutive tasks
+// batch_tasks/batch_task_2932{05..14}.json chain through `parent_batch_hash`; `data_hash` = keccak256 of the chunks' data hashes.
+struct BatchHeader {
+    uint8_t version = 0;
+    uint64_t batch_index = 0, l1_message_popped = 0, total_l1_message_popped = 0, last_block_timestamp = 0;
+    std::array<uint8_t, 32> data_hash{}, blob_versioned_hash{}, parent_batch_hash{}, blob_data_proof[2] = {{}, {}};
+    std::vector<uint8_t> encode() const {
+        std::vector<uint8_t> out;
+        auto be64 = [&](uint64_t v) { for (int b = 7; b >= 0; --b) out.push_back((uint8_t)(v >> (8 * b))); };
+        auto put = [&](const std::array<uint8_t, 32>& a) { out.insert(out.end(), a.begin(), a.end()); };
+        out.push_back(version);
+        be64(batch_index); be64(l1_message_popped); be64(total_l1_message_popped);
+        put(data_hash); put(blob_versioned_hash); put(parent_batch_hash);
+        be64(last_block_timestamp);
+        put(blob_data_proof[0]); put(blob_data_proof[1]);
+        return out;
+    }
+    std::array<uint8_t, 32> batch_hash() const {
+        const std::vector<uint8_t> e = encode();
+        return keccak256(e.data(), e.size());
+    }
+};
+inline BatchHeader parse_batch_header(const protocol::Json& h) {
+    BatchHeader b;
+    b.version = (uint8_t)h.at("version").u64();
+    b.batch_index = h.at("batch_index").u64();
+    b.l1_message_popped = h.at("l1_message_popped").u64();
+    b.total_l1_message_popped = h.at("total_l1_message_popped").u64();
+    b.last_block_timestamp = h.at("last_block_timestamp").u64();
+    b.data_hash = hex32(h.at("data_hash").text);
+    b.blob_versioned_hash = hex32(h.at("blob_versioned_hash").text);
+    b.parent_batch_hash = hex32(h.at("parent_batch_hash").text);
+    if (h.at("blob_data_proof").items.size() != 2) throw std::runtime_error("proof file: blob_data_proof holds two words");
+    for (int i = 0; i < 2; ++i) b.blob_data_proof[i] = hex32(h.at("blob_data_proof").items[i].text);
+    return b;
 }
 
 struct ProofEntry {
@@ -117,15 +170,7 @@ inline ProofEntry parse_entry(const protocol::Json& e) {
     p.instances.push_back(col);
     if (e.has("git_version")) p.git_version = e.at("git_version").text;
     p.is_chunk = e.has("chunk_info");
-    if (p.is_chunk) {
-        const protocol::Json& ci = e.at("chunk_info");
-        p.chunk_info.chain_id = ci.at("chain_id").u64();
-        p.chunk_info.prev_state_root = hex32(ci.at("prev_state_root").text);
-        p.chunk_info.post_state_root = hex32(ci.at("post_state_root").text);
-        p.chunk_info.withdraw_root = hex32(ci.at("withdraw_root").text);
-        p.chunk_info.data_hash = hex32(ci.at("data_hash").text);
-        p.chunk_info.tx_bytes = base64_decode(ci.at("tx_bytes").text);
-    }
+    if (p.is_chunk) p.chunk_info = parse_chunk_info(e.at("chunk_info"));
     if (e.has("batch_hash")) {
         p.has_batch_hash = true;
         p.batch_hash = hex32(e.at("batch_hash").text);
@@ -143,6 +188,37 @@ inline std::vector<ProofEntry> parse_file(const std::string& text) {
         out.push_back(parse_entry(j));
     }
     return out;
+}
+
+// a batch proving task (`BatchProvingTask`: what `gen_batch_proof` takes, /root/reference/integration/src/prove.rs:69): the chunk
+// proofs to aggregate, the chunk infos they were made for, the header of the batch
+struct BatchTask {
+    std::vector<ChunkInfo> chunk_infos;
+    std::vector<ProofEntry> chunk_proofs;
+    BatchHeader header;
+};
+inline BatchTask parse_batch_task(const std::string& text) {
+    protocol::Json j = protocol::JsonParser(text).parse();
+    BatchTask t;
+    for (auto& c : j.at("chunk_infos").items) t.chunk_infos.push_back(parse_chunk_info(c));
+    for (auto& e : j.at("chunk_proofs").items) t.chunk_proofs.push_back(parse_entry(e));
+    t.header = parse_batch_header(j.at("batch_header"));
+    return t;
+}
+// the consistency a batch prover relies on before aggregating: one chunk info per proof and the same one the proof carries, the state
+// roots of consecutive chunks chained, the header's data_hash = keccak256(chunk data hashes)
+inline bool check_batch_task(const BatchTask& t, std::string* why = nullptr) {
+    auto fail = [&](const char* m) { if (why) *why = m; return false; };
+    if (t.chunk_infos.empty() || t.chunk_infos.size() != t.chunk_proofs.size()) return fail("one chunk info per chunk proof");
+    std::vector<uint8_t> hashes;
+    for (size_t i = 0; i < t.chunk_infos.size(); ++i) {
+        if (!t.chunk_proofs[i].is_chunk || t.chunk_infos[i].public_input_hash() != t.chunk_proofs[i].chunk_info.public_input_hash())
+            return fail("a chunk info differs from the one its proof carries");
+        if (i && t.chunk_infos[i].prev_state_root != t.chunk_infos[i - 1].post_state_root) return fail("the chunks' state roots do not chain");
+        hashes.insert(hashes.end(), t.chunk_infos[i].data_hash.begin(), t.chunk_infos[i].data_hash.end());
+    }
+    if (keccak256(hashes.data(), hashes.size()) != t.header.data_hash) return fail("the header's data_hash is not the hash of the chunks' data hashes");
+    return true;
 }
 
 // the verifying key stored beside a proof is the one its protocol was compiled from: k and the fixed + permutation commitments

@@ -5,6 +5,7 @@
 //   --file <proof file> <s_g2 x_c1> <x_c0> <y_c1> <y_c0>: a file AS THE REFERENCE WRITES IT (proof_files.hpp: a chunk / batch proof object
 //   or a container with "chunk_proofs"); one line per proof object, `ACCEPT chunk|batch k=.. proof_bytes=.. git=..` or `REJECT <reason>`,
 //   then `accepted <a> of <n>`; `--tamper` as a 7th argument flips one byte of every proof first.
+//   --batch-task <file>: a batch proving task (chunk_infos, chunk_proofs, batch_header): consistency + the header's batch hash.
 //   --keccak <hex>: Keccak-256 of the message (proof_files.hpp's hash for the chunk public input).
 #include <cstdio>
 #include <fstream>
@@ -68,6 +69,27 @@ static int verify_file(int argc, char** argv) {
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (std::string(argv[1]) == "--file") return argc >= 7 ? verify_file(argc, argv) : 2;
+    if (std::string(argv[1]) == "--batch-task" && argc >= 3) {  // --batch-task <file>: `CONSISTENT|INCONSISTENT <why>` batch_hash=.. parent=.. chunks=..
+        try {
+            std::ifstream f(argv[2], std::ios::binary);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            proof_files::BatchTask t = proof_files::parse_batch_task(ss.str());
+            std::string why;
+            const bool ok = proof_files::check_batch_task(t, &why);
+            auto hex = [](const std::array<uint8_t, 32>& a) {
+                std::string o;
+                char b[3];
+                for (uint8_t v : a) { std::snprintf(b, 3, "%02x", v); o += b; }
+                return o;
+            };
+            std::printf("%s%s%s batch_hash=%s parent=%s chunks=%zu\n", ok ? "CONSISTENT" : "INCONSISTENT ", ok ? "" : why.c_str(), "", hex(t.header.batch_hash()).c_str(),
+                        hex(t.header.parent_batch_hash).c_str(), t.chunk_proofs.size());
+        } catch (const std::exception& e) {
+            std::printf("INCONSISTENT exception: %s\n", e.what());
+        }
+        return 0;
+    }
     if (std::string(argv[1]) == "--keccak") {  // --keccak <hex message>: proof_files::keccak256, for the known-answer test
         std::vector<uint8_t> msg = unhex(argc > 2 ? argv[2] : "");
         auto d = proof_files::keccak256(msg.data(), msg.size());

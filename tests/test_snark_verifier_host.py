@@ -189,3 +189,50 @@ def test_a_batch_proof_carries_its_batch_hash_and_the_second_continues_the_first
     p.write_text(json.dumps(b1))
     accepted, total, lines = verify_file(p)
     assert (accepted, total) == (0, 1) and "batch_hash" in lines[0]
+
+
+def batch_task(path):
+    out = subprocess.run([binary(), "--batch-task", str(path)], capture_output=True, text=True, timeout=120).stdout.strip()
+    fields = dict(kv.split("=") for kv in out.split() if "=" in kv)
+    return out.split()[0], fields, out
+
+
+@have_ref
+def test_batch_tasks_are_consistent_and_their_header_hashes_chain(tmp_path):
+    """proof_files.hpp reads the reference's batch proving tasks (chunk_infos + chunk_proofs + batch_header): every chunk info is the
+    one its proof carries, state roots chain, header.data_hash = keccak(chunk data hashes); BatchHeader::batch_hash (keccak of the
+    193-byte encoding) is pinned by the reference's data twice: the ten consecutive tasks 293205..293214 chain through
+    parent_batch_hash, and the header of full_proof_batch_prove_1.json hashes to the batch_hash of the batch proof made from it."""
+    import glob
+
+    tasks = sorted(glob.glob(os.path.join(DATA, "batch_tasks", "*.json")))
+    assert len(tasks) == 10
+    prev, total = None, 0
+    for f in tasks:
+        verdict, info, out = batch_task(f)
+        assert verdict == "CONSISTENT", out
+        if prev is not None:
+            assert info["parent"] == prev, f
+        prev = info["batch_hash"]
+        total += int(info["chunks"])
+    assert total == 289
+    for name in ("batch-task-no-encode.json", "batch-task-with-blob-raw.json", "batch-task-with-blob.json"):
+        assert batch_task(os.path.join(DATA, name))[0] == "CONSISTENT", name
+    # the batch proof full_proof_batch_agg_1.json was made from the task full_proof_batch_prove_1.json: same batch hash
+    j = json.load(open(os.path.join(DATA, "full_proof_batch_prove_1.json")))
+    j["chunk_infos"] = [cp["chunk_info"] for cp in j["chunk_proofs"]]
+    p = tmp_path / "task.json"
+    p.write_text(json.dumps(j))
+    verdict, info, out = batch_task(p)
+    assert verdict == "CONSISTENT"
+    assert "0x" + info["batch_hash"] == json.load(open(os.path.join(DATA, "full_proof_batch_agg_1.json")))["batch_hash"], out
+    # inconsistencies are named
+    t = json.load(open(tasks[0]))
+    t["chunk_infos"][3]["post_state_root"] = t["chunk_infos"][3]["post_state_root"][:-1] + ("0" if t["chunk_infos"][3]["post_state_root"][-1] != "0" else "1")
+    p.write_text(json.dumps(t))
+    assert batch_task(p)[0] == "INCONSISTENT"
+    t = json.load(open(tasks[0]))
+    t["chunk_infos"], t["chunk_proofs"] = t["chunk_infos"][:-1], t["chunk_proofs"][:-1]
+    p.write_text(json.dumps(t))
+    verdict, _, out = batch_task(p)
+    assert verdict == "INCONSISTENT" and "data_hash" in out
