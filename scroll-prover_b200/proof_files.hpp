@@ -221,6 +221,38 @@ inline bool check_batch_task(const BatchTask& t, std::string* why = nullptr) {
     return true;
 }
 
+// the public input of the batch proof made from a task, after the 12 accumulator limbs: (high, low) 16-byte halves of the first chunk's
+// prev_state_root, the header's parent_batch_hash, the last chunk's post_state_root, the header's batch hash; the chain id; the
+// halves of the last chunk's withdraw_root.  Read off and checked on test_data/full_proof_batch_prove_1.json (task) and
+// full_proof_batch_agg_1.json (the batch proof the reference made from it).
+inline std::vector<Fr> batch_public_input(const BatchTask& t) {
+    if (t.chunk_infos.empty()) throw std::runtime_error("proof file: a batch without chunks");
+    std::vector<Fr> out;
+    auto halves = [&](const std::array<uint8_t, 32>& v) {
+        for (int half = 0; half < 2; ++half) {
+            uint8_t le[32] = {0};
+            for (int b = 0; b < 16; ++b) le[b] = v[16 * half + 15 - b];
+            Fr f;
+            plonk::f_from_repr(le, &f);
+            out.push_back(f);
+        }
+    };
+    halves(t.chunk_infos.front().prev_state_root);
+    halves(t.header.parent_batch_hash);
+    halves(t.chunk_infos.back().post_state_root);
+    halves(t.header.batch_hash());
+    out.push_back(plonk::f_u64(t.chunk_infos.front().chain_id));
+    halves(t.chunk_infos.back().withdraw_root);
+    return out;
+}
+inline bool batch_proof_matches_task(const ProofEntry& batch_proof, const BatchTask& t) {
+    const std::vector<Fr> pi = batch_public_input(t);
+    if (batch_proof.instances.size() != 1 || batch_proof.instances[0].size() != 12 + pi.size()) return false;
+    for (size_t i = 0; i < pi.size(); ++i)
+        if (!(batch_proof.instances[0][12 + i] == pi[i])) return false;
+    return true;
+}
+
 // the verifying key stored beside a proof is the one its protocol was compiled from: k and the fixed + permutation commitments
 inline bool vk_matches_protocol(const ProofEntry& p, std::string* why = nullptr) {
     serde::VerifyingKeyFile vk;

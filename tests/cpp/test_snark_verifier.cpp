@@ -5,7 +5,7 @@
 //   --file <proof file> <s_g2 x_c1> <x_c0> <y_c1> <y_c0>: a file AS THE REFERENCE WRITES IT (proof_files.hpp: a chunk / batch proof object
 //   or a container with "chunk_proofs"); one line per proof object, `ACCEPT chunk|batch k=.. proof_bytes=.. git=..` or `REJECT <reason>`,
 //   then `accepted <a> of <n>`; `--tamper` as a 7th argument flips one byte of every proof first.
-//   --batch-task <file>: a batch proving task (chunk_infos, chunk_proofs, batch_header): consistency + the header's batch hash.
+//   --batch-task <file> [<batch proof file>]: a batch proving task (chunk_infos, chunk_proofs, batch_header): consistency + the header's batch hash.
 //   --keccak <hex>: Keccak-256 of the message (proof_files.hpp's hash for the chunk public input).
 #include <cstdio>
 #include <fstream>
@@ -83,8 +83,15 @@ int main(int argc, char** argv) {
                 for (uint8_t v : a) { std::snprintf(b, 3, "%02x", v); o += b; }
                 return o;
             };
-            std::printf("%s%s%s batch_hash=%s parent=%s chunks=%zu\n", ok ? "CONSISTENT" : "INCONSISTENT ", ok ? "" : why.c_str(), "", hex(t.header.batch_hash()).c_str(),
+            std::printf("%s%s%s batch_hash=%s parent=%s chunks=%zu", ok ? "CONSISTENT" : "INCONSISTENT ", ok ? "" : why.c_str(), "", hex(t.header.batch_hash()).c_str(),
                         hex(t.header.parent_batch_hash).c_str(), t.chunk_proofs.size());
+            if (argc >= 4) {  // a batch proof file: is its public input the one this task determines?
+                std::ifstream g(argv[3], std::ios::binary);
+                std::stringstream s2;
+                s2 << g.rdbuf();
+                std::printf(" proof_matches_task=%d", (int)proof_files::batch_proof_matches_task(proof_files::parse_file(s2.str()).at(0), t));
+            }
+            std::printf("\n");
         } catch (const std::exception& e) {
             std::printf("INCONSISTENT exception: %s\n", e.what());
         }

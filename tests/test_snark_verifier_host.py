@@ -225,6 +225,12 @@ def test_batch_tasks_are_consistent_and_their_header_hashes_chain(tmp_path):
     p.write_text(json.dumps(j))
     verdict, info, out = batch_task(p)
     assert verdict == "CONSISTENT"
+    # and all 11 public inputs of that batch proof are the ones the task determines (roots, hashes, chain id); not those of another task
+    agg = os.path.join(DATA, "full_proof_batch_agg_1.json")
+    out = subprocess.run([binary(), "--batch-task", str(p), agg], capture_output=True, text=True, timeout=120).stdout
+    assert "proof_matches_task=1" in out
+    out = subprocess.run([binary(), "--batch-task", tasks[0], agg], capture_output=True, text=True, timeout=120).stdout
+    assert "proof_matches_task=0" in out
     assert "0x" + info["batch_hash"] == json.load(open(os.path.join(DATA, "full_proof_batch_agg_1.json")))["batch_hash"], out
     # inconsistencies are named
     t = json.load(open(tasks[0]))
